@@ -1,0 +1,136 @@
+/* xm_b200.h — C-ABI of libxm_b200.so: the B200-native (sm_100a) replacement for the hot path of XM's
+ * Burer-Monteiro solver.  Plain C types only; every buffer is caller-owned; no exceptions cross this boundary.
+ *
+ * The reference has no FFI of its own for this path: its pybind11 functions (XM/src/XM_main.cu:403-408) call the
+ * header-only C++ XMtrustregion / checkeig directly.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference tree):
+ *
+ *   xm_set_q_dense      <- loadCMatrixFromBin + opt_var C({3n,3n}); C.SynchronizeHostToDevice   XM/src/XM_main.cu:18-33,189-192
+ *   xm_qy               <- DnMatDnMat (cublasDgemm, M=K=3N, N=r)                                XM/include/Dense/matmul.h:42-87
+ *   xm_trust_region     <- XMtrustregion(C,R0,s0,R,s,lam,gradtol&,ls_step,v,&primal,maxtime)    XM/include/XM/trustregion.h:77-724
+ *   xm_op_*             <- the lambdas objc/grad/projection/ehess+ehess2rhess/retraction        XM/include/XM/trustregion.h:162-351
+ *   xm_certify          <- checkeig(C,sR,lam,v,primal)                                          XM/include/XM/checkeig.h:42-368
+ *   xm_escape_scale     <- DecentDirectionKernal                                                XM/src/XM_main.cu:8-16
+ *
+ * Matrix arguments use the reference's wire layouts: R is 3N x r COLUMN-MAJOR with
+ * rows 3i..3i+2 = camera i; s is length N with s[0] == 1 (the reference's s_ex); v is length 3N.
+ * Host pointers unless the function name ends in _dev (then: device pointers valid on the handle's device).
+ * Return value: XM_OK (0) or a negative XM_E* code.  Numerical exits of the algorithm are NOT errors; they are
+ * reported in xm_stats.exit_code (mirrors the reference's explicit exits, trustregion.h:384-405,527-543,669-700).
+ * One handle = one CUDA device; a handle is not thread-safe.
+ */
+#ifndef XM_B200_H
+#define XM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xm_handle xm_handle;
+
+enum {
+    XM_OK = 0,
+    XM_EINVAL = -1,      /* bad argument (null pointer, r out of [3,XM_MAX_RANK], no Q set, ...) */
+    XM_ECUDA = -2,       /* a CUDA runtime call failed; xm_last_error() has the text */
+    XM_ENOMEM = -3,
+    XM_ENOGPU = -4,      /* no sm_100 device / kernels cannot launch: there is NO CPU fallback */
+    XM_ESYNC = -5,       /* device-side grid barrier timed out (kernel aborted itself) */
+    XM_EUNSUPPORTED = -6
+};
+
+#define XM_MAX_RANK 20
+
+/* xm_stats.exit_code: why xm_trust_region returned */
+enum {
+    XM_EXIT_GRADTOL = 1,      /* gradnorm < gradtol (gradtol_inout is divided by 10, quirk Q1, trustregion.h:532-535) */
+    XM_EXIT_RDOTR_TINY = 2,   /* tCG residual below 1e-15 ("numerical issue", endreason 5, :527-530) */
+    XM_EXIT_MAXTIME = 3,      /* :538-543 */
+    XM_EXIT_MODEL_INCREASE = 4, /* loss_qu >= 0 (:669-672) */
+    XM_EXIT_DELTA_TINY = 5,   /* trust radius < 1e-20 (:697-700) */
+    XM_EXIT_MAX_OUTER = 6,    /* 1000 outer iterations */
+    XM_EXIT_LINESEARCH_FAILED = -1 /* rank-escalation line search failed; primal_out = -1 (:384-405) */
+};
+
+typedef struct xm_options {
+    int device;             /* CUDA device ordinal */
+    int grid_ctas;          /* 0 = auto (<= one CTA per SM); tuning/test hook */
+    int ksplit;             /* 0 = auto; number of k-splits of a camera's Q rows inside a CTA (1,2,4,8,16) */
+    int replicate_stale_sr; /* 1 (default) = reproduce reference quirk Q3 after an accepted line search */
+    int verbose;            /* 1 = print the reference's per-outer-iteration table to stdout after the solve */
+    int max_outer;          /* default 1000 (trustregion.h:417) */
+    int max_inner;          /* default 1000 (trustregion.h:416) */
+    int qy_variant;         /* 0 = auto; dense Q.Y kernel variant (tuning hook) */
+} xm_options;
+
+typedef struct xm_log_rec { /* one line of the reference's stdout table (trustregion.h:487-526) */
+    int k, inner_shown, trstatus, endreason;
+    double loss, gradnorm, delta;
+} xm_log_rec;
+
+typedef struct xm_stats {
+    int exit_code;
+    int outer_iters;        /* value of k at exit */
+    int tcg_iters;          /* the reference's "Total iteration" (sum over outer iterations of i+1) */
+    int qy_products;        /* Q.Y products actually executed on the device */
+    int n_log;              /* number of valid entries in log (<= XM_LOG_CAP) */
+    double primal;          /* loss[k] */
+    double gradnorm;        /* last Riemannian gradient norm */
+    double solve_ms;        /* device time of the persistent solve kernel (CUDA events) */
+    double qy_ms;           /* device time spent inside Q.Y sweeps (globaltimer, CTA 0) */
+    double sync_ms;         /* device time CTA 0 spent waiting in grid barriers */
+    int grid_ctas, threads_per_cta, ksplit, launches; /* launch configuration actually used / kernels launched */
+} xm_stats;
+
+#define XM_LOG_CAP 1002
+
+void xm_default_options(xm_options* opt);
+int  xm_create(xm_handle** out, const xm_options* opt);
+int  xm_destroy(xm_handle* h);
+const char* xm_last_error(const xm_handle* h);
+/* stream: a cudaStream_t (as void*) on the handle's device; NULL = the legacy default stream. */
+int  xm_set_stream(xm_handle* h, void* cuda_stream);
+
+/* Q: n3 x n3 (n3 = 3N) column-major with leading dimension ld >= n3.  Copied (and re-laid-out) into HBM. */
+int  xm_set_q_dense(xm_handle* h, int n3, const double* q_colmajor, int64_t ld);
+int  xm_set_q_dense_dev(xm_handle* h, int n3, const double* q_colmajor_dev, int64_t ld);
+/* Block-CSR Q with bdim x bdim blocks (bdim in {3,4}); nb block rows; block values column-major per block. */
+int  xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, const int* colidx, const double* vals);
+
+/* out = alpha * Q * X ; X, out: 3N x r column-major (ld = 3N). */
+int  xm_qy(xm_handle* h, int r, double alpha, const double* X, double* out);
+int  xm_qy_dev(xm_handle* h, int r, double alpha, const double* X_dev, double* out_dev);
+
+/* Mirrors XMtrustregion.  R0/R_out: 3N x r col-major; s0/s_out: length N (s[0] = 1); v: length 3N or NULL when
+ * ls_step == 0.  gradtol_inout is updated like the reference's by-reference gradtol.  stats/log may be NULL. */
+int  xm_trust_region(xm_handle* h, int r, const double* R0, const double* s0, double lam,
+                     double* gradtol_inout, double ls_step, const double* v, double max_time,
+                     double* R_out, double* s_out, double* primal_out, xm_stats* stats, xm_log_rec* log);
+int  xm_trust_region_dev(xm_handle* h, int r, const double* R0_dev, const double* s0_dev, double lam,
+                     double* gradtol_inout, double ls_step, const double* v_dev, double max_time,
+                     double* R_out_dev, double* s_out_dev, double* primal_out, xm_stats* stats, xm_log_rec* log);
+
+/* Op-level hooks (unit-test surface; same device code as the solver phases). All R-like args 3N x r col-major. */
+int  xm_op_objective(xm_handle* h, int r, const double* R, const double* s, double lam, double* f_out);
+/* Riemannian gradient at (R,s): rgradR (3N x r), rgrads (N, [0]=0); also returns egrad pieces if non-NULL. */
+int  xm_op_rgrad(xm_handle* h, int r, const double* R, const double* s, double lam,
+                 double* rgradR, double* rgrads, double* gradnorm_out);
+/* Riemannian Hessian-vector product at (R,s) along (P,ps) (ps[0] ignored -> 0): HpR (3N x r), Hps (N). */
+int  xm_op_rhess(xm_handle* h, int r, const double* R, const double* s, double lam,
+                 const double* P, const double* ps, double* HpR, double* Hps);
+/* Retraction: Rn = MGS(R + lr*etaR) per camera ; sn = s * exp(lr*etas/s). */
+int  xm_op_retract(xm_handle* h, int r, const double* R, const double* s, const double* etaR,
+                   const double* etas, double lr, double* Rn, double* sn);
+
+/* Optimality certificate (checkeig): sR = R*s is formed internally.  v_out (3N) = eigenvector of the minimum
+ * eigenvalue of the dual slack.  certified_out: 1/0. */
+int  xm_certify(xm_handle* h, int r, const double* R, const double* s, double lam, double primal,
+                double* v_out, double* min_eig_out, double* dual_out, double* gap_out, int* certified_out);
+/* v[3i..3i+2] /= s[i]  (DecentDirectionKernal) — host-side helper, trivial. */
+int  xm_escape_scale(int n_cameras, double* v, const double* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XM_B200_H */

@@ -1,0 +1,115 @@
+"""GPU parity, op level: every device phase against the oracle on seeded random inputs, through the C-ABI.
+Tolerance for this FP64 path: 1e-12 relative; the operation order differs from the reference's
+cuBLAS calls, so bit-exactness is not defined."""
+import numpy as np
+import pytest
+
+from oracle import xm_oracle as xo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1e-300, np.max(np.abs(b))))
+
+
+def rand_psd(n3, rng):
+    A = rng.standard_normal((n3, n3 + 3))
+    return A @ A.T / n3
+
+
+def rand_point(N, r, rng):
+    Y = xo.mgs_rows(rng.standard_normal((N, 3, r)))
+    s = np.concatenate([[1.0], rng.uniform(0.7, 1.4, N - 1)])
+    return Y, s
+
+
+CASES = [(1, 3), (2, 3), (5, 4), (33, 3), (64, 5), (149, 3), (150, 7), (301, 10), (77, 13), (40, 20), (500, 3), (700, 6)]
+
+
+@pytest.mark.parametrize("N,r", CASES)
+def test_qy_matches_oracle(gpu_handle_factory, N, r):
+    rng = np.random.default_rng(100 + N + r)
+    Q = rand_psd(3 * N, rng)
+    Q = Q + 0.1 * rng.standard_normal(Q.shape)        # deliberately NOT symmetric: out = Q X, not Q^T X
+    h = gpu_handle_factory()
+    h.set_q_dense(Q)
+    X = rng.standard_normal((3 * N, r))
+    got = h.qy(X, alpha=2.0)
+    assert rel(got, 2.0 * Q @ X) < TOL
+
+
+@pytest.mark.parametrize("grid,ks", [(1, 1), (1, 16), (3, 4), (16, 2), (148, 0), (40, 8)])
+def test_qy_launch_geometries(gpu_handle_factory, grid, ks):
+    rng = np.random.default_rng(7)
+    N, r = 97, 5
+    Q = rand_psd(3 * N, rng)
+    X = rng.standard_normal((3 * N, r))
+    h = gpu_handle_factory(grid_ctas=grid, ksplit=ks)
+    h.set_q_dense(Q)
+    assert rel(h.qy(X), Q @ X) < TOL
+
+
+def test_qy_strided_ld_and_reupload(gpu_handle_factory):
+    rng = np.random.default_rng(8)
+    N = 20
+    big = rng.standard_normal((3 * N + 5, 3 * N))
+    bigF = np.asfortranarray(big)                      # keep alive: the pointer below refers to it
+    Q = bigF[: 3 * N, :]                                # column-major view with ld = 3N + 5
+    h = gpu_handle_factory()
+    h.set_q_dense_ptr(3 * N, bigF.ctypes.data, ld=3 * N + 5)
+    X = rng.standard_normal((3 * N, 3))
+    assert rel(h.qy(X), Q @ X) < TOL
+    Q2 = rand_psd(3 * 31, rng)                          # different size on the same handle
+    h.set_q_dense(Q2)
+    X2 = rng.standard_normal((93, 4))
+    assert rel(h.qy(X2), Q2 @ X2) < TOL
+
+
+@pytest.mark.parametrize("N,r,lam", [(2, 3, 0.0), (9, 3, 0.5), (64, 5, 0.0), (149, 4, 0.1), (333, 8, 0.0), (50, 16, 0.2)])
+def test_objective_gradient_hessian_retraction(gpu_handle_factory, N, r, lam):
+    rng = np.random.default_rng(200 + N + r)
+    Q = rand_psd(3 * N, rng)
+    Y, s = rand_point(N, r, rng)
+    R = xo.from_blocks(Y)
+    h = gpu_handle_factory()
+    h.set_q_dense(Q)
+    # objective (trustregion.h:162-170)
+    f = h.objective(R, s, lam)
+    assert abs(f - xo.objective(Q, Y, s, lam)) < TOL * abs(f) * 10
+    # Riemannian gradient (grad :186-194 + projection :307-317)
+    D, G, g = xo.egrad(Q, Y, s, lam)
+    rgR, rgs = xo.project(Y, s, G, g)
+    gR, gs, gn = h.rgrad(R, s, lam)
+    assert rel(gR, xo.from_blocks(rgR)) < TOL * 10
+    assert rel(gs, rgs) < TOL * 10 and gs[0] == 0.0
+    ref_gn = np.sqrt(np.vdot(rgR, rgR) + np.sum((rgs[1:] / s[1:]) ** 2))
+    assert abs(gn - ref_gn) < TOL * 10 * ref_gn
+    # Riemannian Hessian-vector (ehess :227-255 + ehess2rhess :277-295)
+    P = rng.standard_normal(Y.shape)
+    ps = rng.standard_normal(N); ps[0] = 0.0
+    HR, Hs = xo.rhess_vec(Q, Y, s, lam, D, G, g, P, ps)
+    gHR, gHs = h.rhess(R, s, xo.from_blocks(P), ps, lam)
+    assert rel(gHR, xo.from_blocks(HR)) < TOL * 10
+    assert rel(gHs, Hs) < TOL * 10
+    # retraction (:341-351, batchedQR.h:42-67)
+    eta = 0.3 * rng.standard_normal(Y.shape); es = 0.2 * rng.standard_normal(N)
+    Yn, sn = xo.retract(Y, s, eta, es, 0.7)
+    gRn, gsn = h.retract(R, s, xo.from_blocks(eta), es, 0.7)
+    assert rel(gRn, xo.from_blocks(Yn)) < TOL * 10
+    assert rel(gsn, sn) < TOL * 10 and gsn[0] == 1.0
+
+
+def test_bsr_operator_matches_dense(gpu_handle_factory):
+    from xm_code_b200 import problems
+    rowptr, col, vals = problems.erdos_renyi_bsr(120, avg_degree=10, seed=4)
+    Q = problems.bsr_to_dense(rowptr, col, vals)
+    rng = np.random.default_rng(3)
+    h = gpu_handle_factory()
+    h.set_q_bsr(rowptr, col, vals, 3)
+    for r in (3, 5, 10):
+        X = rng.standard_normal((360, r))
+        assert rel(h.qy(X, 0.5), 0.5 * Q @ X) < TOL
+    Y, s = rand_point(120, 4, rng)
+    assert abs(h.objective(xo.from_blocks(Y), s, 0.0) - xo.objective(Q, Y, s, 0.0)) < 1e-11 * abs(xo.objective(Q, Y, s, 0.0))

@@ -1,0 +1,154 @@
+"""GPU parity, solver level: the persistent trust-region kernel against the oracle (which is itself pinned against
+the reference's own output, tests/test_oracle_vs_reference.py) on the reference's shipped inputs, plus the pybind11
+module end to end."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import xm_oracle as xo
+from conftest import anchored_gram, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def check_point(got, ref, primal_rel=1e-10, s_abs=1e-8, x_abs=1e-7):
+    assert abs(got.primal - ref.primal) <= primal_rel * abs(ref.primal)
+    np.testing.assert_allclose(got.s, ref.s, atol=s_abs, rtol=0)
+    np.testing.assert_allclose(anchored_gram(got.R, got.s), anchored_gram(xo.from_blocks(ref.Y), ref.s), atol=x_abs, rtol=0)
+
+
+def test_simple1_rank3_matches_oracle(gpu_handle_factory, simple1_q):
+    N = simple1_q.shape[0] // 3
+    h = gpu_handle_factory()
+    h.set_q_dense(simple1_q)
+    got = h.trust_region(xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.0, 1e-16)
+    ref = xo.trust_region(simple1_q, xo.identity_init(N, 3), np.ones(N), 0.0, 1e-16)
+    assert abs(got.primal - 2.550991567720) < 5e-11          # certified global optimum
+    check_point(got, ref)
+    # same trajectory: identical outer-iteration table while the problem is well conditioned
+    assert got.stats["outer_iters"] == ref.outer_iters == 13
+    for a, b in zip(got.log[:11], ref.log[:11]):
+        assert a[0] == b[0] and a[1] == b[1] and a[4] == b[4] and a[5] == b[5]
+        assert abs(a[2] - b[2]) <= 1e-9 * abs(b[2]) and abs(a[3] - b[3]) <= 1e-6 * abs(b[3])
+    assert got.stats["exit"] == "rdotr_tiny" and got.gradtol == 1e-16
+    assert got.stats["qy_products"] > got.stats["tcg_iters"] - got.stats["outer_iters"]
+
+
+def test_simple2_matches_oracle(gpu_handle_factory, simple2_q):
+    N = simple2_q.shape[0] // 3
+    h = gpu_handle_factory()
+    h.set_q_dense(simple2_q)
+    for tol in (1e-1, 1e-10):
+        got = h.trust_region(xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.0, tol)
+        ref = xo.trust_region(simple2_q, xo.identity_init(N, 3), np.ones(N), 0.0, tol)
+        assert got.stats["outer_iters"] == ref.outer_iters
+        check_point(got, ref, primal_rel=1e-9 if tol > 1e-5 else 1e-10, s_abs=1e-7 if tol > 1e-5 else 1e-8)
+        assert got.gradtol == pytest.approx(tol / 10)     # quirk Q1
+    assert abs(got.primal - 4.8322430007e-02) < 1e-10
+
+
+def test_regulariser_and_geometries(gpu_handle_factory):
+    from xm_code_b200 import problems
+    Q, prob = problems.synthetic_dense_q(80, seed=5)
+    N = 80
+    ref = xo.trust_region(Q, xo.identity_init(N, 3), np.ones(N), 0.05, 1e-8)
+    for kw in (dict(), dict(grid_ctas=1), dict(grid_ctas=7, ksplit=2), dict(grid_ctas=80, ksplit=16)):
+        h = gpu_handle_factory(**kw)
+        h.set_q_dense(Q)
+        got = h.trust_region(xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.05, 1e-8)
+        check_point(got, ref, primal_rel=1e-9, s_abs=1e-7, x_abs=1e-6)
+
+
+def test_rank_escalation_line_search_path(gpu_handle_factory):
+    """Replays an r -> r+1 escalation (XM_main.cu:265-271 + trustregion.h:360-408) with identical inputs on both sides,
+    including quirk Q3 (stale sR after an accepted line search)."""
+    rng = np.random.default_rng(11)
+    N = 30
+    A = rng.standard_normal((3 * N, 3 * N + 2))
+    Q = A @ A.T / (3 * N)                     # generic PSD matrix: rank 3 is not tight, escalation does real work
+    h = gpu_handle_factory()
+    h.set_q_dense(Q)
+    res3 = xo.trust_region(Q, xo.identity_init(N, 3), np.ones(N), 0.0, 1e-7)
+    c = xo.certificate(Q, xo.from_blocks(res3.Y * res3.s[:, None, None]), 0.0, res3.primal)
+    assert not c["certified"]
+    Y0 = np.concatenate([res3.Y, np.zeros((N, 3, 1))], axis=2)
+    v = (c["v"].reshape(N, 3) / res3.s[:, None]).reshape(-1)
+    ref = xo.trust_region(Q, Y0, res3.s, 0.0, 1e-7, ls_step=1.0, v=v)
+    got = h.trust_region(xo.from_blocks(Y0), res3.s, 0.0, 1e-7, ls_step=1.0, v=v)
+    assert ref.status == 0 and ref.primal < res3.primal
+    assert got.log[0][2] == pytest.approx(ref.log[0][2], rel=1e-12)      # loss[0] is the stale f0 (Q3)
+    assert abs(got.primal - ref.primal) <= 1e-8 * abs(ref.primal)
+    # a direction whose trial objective is not below f0 (NaN compares false both ways) -> line search failure,
+    # primal = -1 (trustregion.h:394-405); deterministic on both sides
+    Yopt = np.concatenate([ref.Y, np.zeros((N, 3, 1))], axis=2)
+    bad = h.trust_region(xo.from_blocks(Yopt), ref.s, 0.0, 1e-7, ls_step=1.0, v=np.full(3 * N, np.nan))
+    assert bad.primal == -1.0 and bad.stats["exit"] == "linesearch_failed"
+    bad_ref = xo.trust_region(Q, Yopt, ref.s, 0.0, 1e-7, ls_step=1.0, v=np.full(3 * N, np.nan))
+    assert bad_ref.primal == -1.0
+
+
+def test_certificate_matches_oracle(gpu_handle_factory, simple1_q):
+    N = simple1_q.shape[0] // 3
+    h = gpu_handle_factory()
+    h.set_q_dense(simple1_q)
+    got = h.trust_region(xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.0, 1e-16)
+    c = h.certify(got.R, got.s, 0.0, got.primal)
+    ref = xo.certificate(simple1_q, got.R * np.repeat(got.s, 3)[:, None], 0.0, got.primal)
+    assert c["certified"] and ref["certified"]
+    assert abs(c["min_eig"] - ref["min_eig"]) < 1e-8 and abs(c["dual"] - ref["dual"]) < 1e-7
+    # a non-tight case: the eigenvector must be a descent direction (sign-free) with the same eigenvalue
+    rng = np.random.default_rng(12)
+    A = rng.standard_normal((60, 62)); Q = A @ A.T / 60
+    h.set_q_dense(Q)
+    r3 = h.trust_region(xo.from_blocks(xo.identity_init(20, 3)), np.ones(20), 0.0, 1e-8)
+    c = h.certify(r3.R, r3.s, 0.0, r3.primal)
+    ref = xo.certificate(Q, r3.R * np.repeat(r3.s, 3)[:, None], 0.0, r3.primal)
+    assert c["certified"] == ref["certified"]
+    assert abs(c["min_eig"] - ref["min_eig"]) < 1e-8 * max(1.0, abs(ref["min_eig"]))
+    assert min(np.abs(c["v"] - ref["v"]).max(), np.abs(c["v"] + ref["v"]).max()) < 1e-6
+
+
+def test_xm_module_runs_the_reference_demo_call(tmp_path, simple1_q):
+    """What 1_test_solve.py does (XM.solve(path, 3, 1e-16, 0.0, 1000)), through the compiled pybind11 module."""
+    from xm_code_b200 import binio
+    d = tmp_path / "SIMPLE1"
+    d.mkdir()
+    binio.save_matrix_to_bin(str(d / "Q.bin"), simple1_q)
+    code = ("import sys; sys.path.append(%r); import XM; XM.solve(%r, 3, 1e-16, 0.0, 1000); "
+            "print('status', XM.solve_rebuttle(%r, 4, 1e-6, 0.0, 1000)); XM.solve_rank3(%r, 3, 1e-6, 0.0, 1000)") % (
+        os.path.join(ROOT, "XM", "build"), str(d) + "/", str(d), str(d))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "BM finished with rank 3" in out.stdout and "status 1" in out.stdout
+    R = binio.load_matrix_from_bin(str(d / "R.bin")); s = binio.load_matrix_from_bin(str(d / "s.bin"))
+    assert R.shape == (447, 3) and s.shape == (149, 1) and s[0, 0] == 1.0
+    ref = xo.solve(simple1_q, 3, 1e-6, 0.0, rank3_only=True)
+    np.testing.assert_allclose(s[:, 0], ref["s"], atol=1e-6)
+
+
+def test_full_size_properties_bal_shaped(gpu_handle_factory):
+    """BASELINE-size check through size-independent properties (the oracle would take minutes here):
+    feasibility of the returned point, monotone accepted losses, optimality (small Riemannian gradient via the op
+    hook), agreement of the objective with an independent NumPy evaluation, and run-to-run determinism."""
+    from xm_code_b200 import problems
+    Q, prob = problems.synthetic_dense_q(1723, seed=0, obs_per_camera=60, n_landmarks=12 * 1723)
+    N = 1723
+    h = gpu_handle_factory()
+    h.set_q_dense(Q)
+    R0 = xo.from_blocks(xo.identity_init(N, 3))
+    a = h.trust_region(R0, np.ones(N), 0.0, 1e-6)
+    b = h.trust_region(R0, np.ones(N), 0.0, 1e-6)
+    assert a.stats["exit"] == "gradtol"
+    assert np.array_equal(a.R, b.R) and np.array_equal(a.s, b.s) and a.primal == b.primal      # deterministic
+    Y = xo.to_blocks(a.R)
+    np.testing.assert_allclose(np.einsum("iaj,ibj->iab", Y, Y), np.broadcast_to(np.eye(3), (N, 3, 3)), atol=1e-12)
+    sR = a.R * np.repeat(a.s, 3)[:, None]
+    assert abs(float(np.vdot(Q @ sR, sR)) - a.primal) <= 1e-10 * abs(a.primal)
+    losses = [l[2] for l in a.log]
+    assert all(x >= y - 1e-12 * abs(x) for x, y in zip(losses, losses[1:]))
+    _, _, gn = h.rgrad(a.R, a.s, 0.0)
+    assert gn < 1e-6
+    assert np.max(np.abs(a.s - prob["s"])) < 5e-2                # recovers the ground-truth scales up to noise

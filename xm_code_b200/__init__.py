@@ -1,0 +1,16 @@
+"""xm_code_b200 — B200-native (sm_100a) implementation of the XM Burer-Monteiro trust-region path.
+
+Host-side Python mirror of the reference surface for this path only:
+
+  * ``capi``      ctypes binding of the C-ABI (include/xm_b200.h, libxm_b200.so) — what tests and bench.py call
+  * ``solver``    ``solve`` / ``solve_rank3`` / ``solve_rebuttle`` with the reference's path-based semantics
+                  (XM/src/XM_main.cu:35-401), driving the C-ABI
+  * ``binio``     the ``.bin`` wire format (utils/io.py:17-58)
+  * ``problems``  synthetic Q generators for the BASELINE configs (no reference code involved)
+
+The compiled pybind11 module ``XM`` (XM/build/, built by XM/CMakeLists.txt or __graft_entry__.build()) exposes the
+same three functions from C++ for the reference's demo scripts.  Nothing in this package imports ``oracle/``.
+"""
+from . import binio  # noqa: F401
+
+__all__ = ["binio", "capi", "solver", "problems"]

@@ -1,0 +1,247 @@
+"""ctypes binding of the C-ABI in include/xm_b200.h (libxm_b200.so).
+
+Fails loudly: if the shared library is missing or no sm_100 GPU is present there is NO fallback — ``load()`` /
+``Handle()`` raise.  Arrays cross the boundary in the reference's wire layouts (3N x r column-major, s length N)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxm_b200.so")
+XM_LOG_CAP = 1002
+XM_MAX_RANK = 20
+
+ERRORS = {0: "XM_OK", -1: "XM_EINVAL", -2: "XM_ECUDA", -3: "XM_ENOMEM", -4: "XM_ENOGPU", -5: "XM_ESYNC", -6: "XM_EUNSUPPORTED"}
+EXIT_CODES = {1: "gradtol", 2: "rdotr_tiny", 3: "maxtime", 4: "model_increase", 5: "delta_tiny", 6: "max_outer", -1: "linesearch_failed", 0: "none"}
+
+
+class XmOptions(C.Structure):
+    _fields_ = [("device", C.c_int), ("grid_ctas", C.c_int), ("ksplit", C.c_int), ("replicate_stale_sr", C.c_int),
+                ("verbose", C.c_int), ("max_outer", C.c_int), ("max_inner", C.c_int), ("qy_variant", C.c_int)]
+
+
+class XmLogRec(C.Structure):
+    _fields_ = [("k", C.c_int), ("inner_shown", C.c_int), ("trstatus", C.c_int), ("endreason", C.c_int),
+                ("loss", C.c_double), ("gradnorm", C.c_double), ("delta", C.c_double)]
+
+
+class XmStats(C.Structure):
+    _fields_ = [("exit_code", C.c_int), ("outer_iters", C.c_int), ("tcg_iters", C.c_int), ("qy_products", C.c_int),
+                ("n_log", C.c_int), ("primal", C.c_double), ("gradnorm", C.c_double), ("solve_ms", C.c_double),
+                ("qy_ms", C.c_double), ("sync_ms", C.c_double), ("grid_ctas", C.c_int), ("threads_per_cta", C.c_int),
+                ("ksplit", C.c_int), ("launches", C.c_int)]
+
+
+EXPORTS = [
+    "xm_default_options", "xm_create", "xm_destroy", "xm_last_error", "xm_set_stream", "xm_set_q_dense",
+    "xm_set_q_dense_dev", "xm_set_q_bsr", "xm_qy", "xm_qy_dev", "xm_trust_region", "xm_trust_region_dev",
+    "xm_op_objective", "xm_op_rgrad", "xm_op_rhess", "xm_op_retract", "xm_certify", "xm_escape_scale", "xm_bench_qy",
+]
+
+_lib = None
+
+
+def load(path: str | None = None):
+    """dlopen libxm_b200.so (raises OSError if it has not been built: run ``python __graft_entry__.py``)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise OSError(f"{p} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                      "there is no CPU fallback for the XM hot path")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    dp = C.POINTER(C.c_double)
+    vp = C.c_void_p
+    lib.xm_default_options.argtypes = [C.POINTER(XmOptions)]
+    lib.xm_default_options.restype = None
+    lib.xm_create.argtypes = [C.POINTER(vp), C.POINTER(XmOptions)]
+    lib.xm_destroy.argtypes = [vp]
+    lib.xm_last_error.argtypes = [vp]
+    lib.xm_last_error.restype = C.c_char_p
+    lib.xm_set_stream.argtypes = [vp, vp]
+    lib.xm_set_q_dense.argtypes = [vp, C.c_int, vp, C.c_int64]
+    lib.xm_set_q_dense_dev.argtypes = [vp, C.c_int, vp, C.c_int64]
+    lib.xm_set_q_bsr.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.xm_qy.argtypes = [vp, C.c_int, C.c_double, vp, vp]
+    lib.xm_qy_dev.argtypes = [vp, C.c_int, C.c_double, vp, vp]
+    tr_args = [vp, C.c_int, vp, vp, C.c_double, dp, C.c_double, vp, C.c_double, vp, vp, dp, C.POINTER(XmStats), vp]
+    lib.xm_trust_region.argtypes = tr_args
+    lib.xm_trust_region_dev.argtypes = tr_args
+    lib.xm_op_objective.argtypes = [vp, C.c_int, vp, vp, C.c_double, dp]
+    lib.xm_op_rgrad.argtypes = [vp, C.c_int, vp, vp, C.c_double, vp, vp, dp]
+    lib.xm_op_rhess.argtypes = [vp, C.c_int, vp, vp, C.c_double, vp, vp, vp, vp]
+    lib.xm_op_retract.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_double, vp, vp]
+    lib.xm_certify.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, dp, dp, dp, C.POINTER(C.c_int)]
+    lib.xm_escape_scale.argtypes = [C.c_int, vp, vp]
+    lib.xm_bench_qy.argtypes = [vp, C.c_int, C.c_int, dp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("xm_default_options", "xm_last_error"):
+            fn.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class XmError(RuntimeError):
+    pass
+
+
+def _f64(a, order="F"):
+    return np.require(np.asarray(a, dtype=np.float64), requirements=["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS", "ALIGNED"])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class TRResult:
+    R: np.ndarray          # 3N x r
+    s: np.ndarray          # N, s[0] == 1
+    primal: float
+    gradtol: float
+    stats: dict
+    log: list
+
+
+class Handle:
+    """One xm_handle (one CUDA device)."""
+
+    def __init__(self, device: int = 0, grid_ctas: int = 0, ksplit: int = 0, replicate_stale_sr: bool = True,
+                 verbose: bool = False, max_outer: int = 1000, max_inner: int = 1000):
+        self.lib = load()
+        opt = XmOptions()
+        self.lib.xm_default_options(C.byref(opt))
+        opt.device = device; opt.grid_ctas = grid_ctas; opt.ksplit = ksplit
+        opt.replicate_stale_sr = int(replicate_stale_sr); opt.verbose = int(verbose)
+        opt.max_outer = max_outer; opt.max_inner = max_inner
+        self._h = C.c_void_p()
+        rc = self.lib.xm_create(C.byref(self._h), C.byref(opt))
+        if rc != 0:
+            raise XmError(f"xm_create failed: {ERRORS.get(rc, rc)} (an sm_100 GPU is required; no CPU fallback)")
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.xm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.xm_last_error(self._h)
+            raise XmError(f"{what}: {ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.xm_set_stream(self._h, C.c_void_p(cuda_stream)), "xm_set_stream")
+
+    # ---- operator
+    def set_q_dense(self, Q):
+        Q = _f64(Q)
+        n3 = Q.shape[0]
+        self._check(self.lib.xm_set_q_dense(self._h, n3, _ptr(Q), n3), "xm_set_q_dense")
+        self.N = n3 // 3
+
+    def set_q_dense_ptr(self, n3: int, host_ptr: int, ld: int | None = None):
+        self._check(self.lib.xm_set_q_dense(self._h, n3, C.c_void_p(host_ptr), ld or n3), "xm_set_q_dense")
+        self.N = n3 // 3
+
+    def set_q_dense_dev(self, n3: int, dev_ptr: int, ld: int | None = None):
+        self._check(self.lib.xm_set_q_dense_dev(self._h, n3, C.c_void_p(dev_ptr), ld or n3), "xm_set_q_dense_dev")
+        self.N = n3 // 3
+
+    def set_q_bsr(self, rowptr, colidx, vals, bdim: int):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        nb = rowptr.size - 1
+        self._check(self.lib.xm_set_q_bsr(self._h, nb, bdim, _ptr(rowptr), _ptr(colidx), _ptr(vals)), "xm_set_q_bsr")
+        self.N = nb
+
+    # ---- ops
+    def qy(self, X, alpha: float = 1.0):
+        X = _f64(X)
+        out = np.empty_like(X, order="F")
+        self._check(self.lib.xm_qy(self._h, X.shape[1], alpha, _ptr(X), _ptr(out)), "xm_qy")
+        return out
+
+    def qy_dev(self, r: int, x_dev_ptr: int, out_dev_ptr: int, alpha: float = 1.0):
+        self._check(self.lib.xm_qy_dev(self._h, r, alpha, C.c_void_p(x_dev_ptr), C.c_void_p(out_dev_ptr)), "xm_qy_dev")
+
+    def bench_qy(self, r: int, iters: int) -> float:
+        ms = C.c_double()
+        self._check(self.lib.xm_bench_qy(self._h, r, iters, C.byref(ms)), "xm_bench_qy")
+        return ms.value
+
+    def objective(self, R, s, lam=0.0) -> float:
+        R = _f64(R); s = _f64(s)
+        f = C.c_double()
+        self._check(self.lib.xm_op_objective(self._h, R.shape[1], _ptr(R), _ptr(s), lam, C.byref(f)), "xm_op_objective")
+        return f.value
+
+    def rgrad(self, R, s, lam=0.0):
+        R = _f64(R); s = _f64(s)
+        gR = np.empty_like(R, order="F"); gs = np.empty_like(s)
+        gn = C.c_double()
+        self._check(self.lib.xm_op_rgrad(self._h, R.shape[1], _ptr(R), _ptr(s), lam, _ptr(gR), _ptr(gs), C.byref(gn)), "xm_op_rgrad")
+        return gR, gs, gn.value
+
+    def rhess(self, R, s, P, ps, lam=0.0):
+        R = _f64(R); s = _f64(s); P = _f64(P); ps = _f64(ps)
+        HR = np.empty_like(R, order="F"); Hs = np.empty_like(s)
+        self._check(self.lib.xm_op_rhess(self._h, R.shape[1], _ptr(R), _ptr(s), lam, _ptr(P), _ptr(ps), _ptr(HR), _ptr(Hs)), "xm_op_rhess")
+        return HR, Hs
+
+    def retract(self, R, s, etaR, etas, lr=1.0):
+        R = _f64(R); s = _f64(s); etaR = _f64(etaR); etas = _f64(etas)
+        Rn = np.empty_like(R, order="F"); sn = np.empty_like(s)
+        self._check(self.lib.xm_op_retract(self._h, R.shape[1], _ptr(R), _ptr(s), _ptr(etaR), _ptr(etas), lr, _ptr(Rn), _ptr(sn)), "xm_op_retract")
+        return Rn, sn
+
+    # ---- solver
+    def trust_region(self, R0, s0, lam=0.0, gradtol=1e-6, ls_step=0.0, v=None, max_time=1000.0) -> TRResult:
+        R0 = _f64(R0); s0 = _f64(s0)
+        r = R0.shape[1]
+        R = np.empty_like(R0, order="F"); s = np.empty_like(s0)
+        gt = C.c_double(gradtol); primal = C.c_double()
+        st = XmStats()
+        log = (XmLogRec * XM_LOG_CAP)()
+        vv = _f64(v) if v is not None else None
+        rc = self.lib.xm_trust_region(self._h, r, _ptr(R0), _ptr(s0), lam, C.byref(gt), ls_step,
+                                      _ptr(vv) if vv is not None else None, max_time, _ptr(R), _ptr(s),
+                                      C.byref(primal), C.byref(st), C.cast(log, C.c_void_p))
+        self._check(rc, "xm_trust_region")
+        stats = {f[0]: getattr(st, f[0]) for f in XmStats._fields_}
+        stats["exit"] = EXIT_CODES.get(st.exit_code, str(st.exit_code))
+        lg = [(log[i].k, log[i].inner_shown, log[i].loss, log[i].gradnorm, log[i].trstatus, log[i].endreason, log[i].delta)
+              for i in range(st.n_log)]
+        return TRResult(R=R, s=s, primal=primal.value, gradtol=gt.value, stats=stats, log=lg)
+
+    def trust_region_dev(self, r, R0_ptr, s0_ptr, R_ptr, s_ptr, lam=0.0, gradtol=1e-6, ls_step=0.0, v_ptr=None, max_time=1000.0):
+        gt = C.c_double(gradtol); primal = C.c_double()
+        st = XmStats()
+        rc = self.lib.xm_trust_region_dev(self._h, r, C.c_void_p(R0_ptr), C.c_void_p(s0_ptr), lam, C.byref(gt), ls_step,
+                                          C.c_void_p(v_ptr) if v_ptr else None, max_time, C.c_void_p(R_ptr), C.c_void_p(s_ptr),
+                                          C.byref(primal), C.byref(st), None)
+        self._check(rc, "xm_trust_region_dev")
+        stats = {f[0]: getattr(st, f[0]) for f in XmStats._fields_}
+        stats["exit"] = EXIT_CODES.get(st.exit_code, str(st.exit_code))
+        return primal.value, gt.value, stats
+
+    def certify(self, R, s, lam, primal):
+        R = _f64(R); s = _f64(s)
+        v = np.empty(R.shape[0]); me = C.c_double(); du = C.c_double(); gap = C.c_double(); cert = C.c_int()
+        self._check(self.lib.xm_certify(self._h, R.shape[1], _ptr(R), _ptr(s), lam, primal, _ptr(v), C.byref(me), C.byref(du),
+                                        C.byref(gap), C.byref(cert)), "xm_certify")
+        return dict(certified=bool(cert.value), min_eig=me.value, dual=du.value, gap=gap.value, v=v)

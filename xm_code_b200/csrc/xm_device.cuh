@@ -1,0 +1,418 @@
+// xm_device.cuh — sm_100a device code of the XM Burer-Monteiro trust-region path.
+//
+// One persistent cooperative kernel runs a whole XMtrustregion call (reference: XM/include/XM/trustregion.h:77-724)
+// with zero host round trips: every CTA owns a contiguous range of cameras for ALL per-camera work, the only
+// cross-CTA data are the Q.Y operand (j-major, written once per tCG iteration) and one double per CTA per
+// reduction.  Scalars (alpha, beta, tau, rho, Delta ...) are recomputed redundantly and bit-identically by every
+// CTA from the same per-CTA partial sums in the same order, so control flow is grid-uniform and reductions are
+// deterministic run to run.
+//
+// Layouts:
+//   camera-block  V[(3i+a)*r + j]      — all state vectors (the reference's "o x 3N" R_T layout, camera contiguous)
+//   j-major       Xt[j*ldq + 3i+a]     — Q.Y operand (the reference's "3N x o" column-major layout, ld padded)
+//   Q             Qp[i*ldq + k]        — dense, row-major, rows padded to ldq (multiple of 64 doubles, zero filled)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xm {
+
+constexpr int kMaxRank = 20;
+constexpr int kLogCap = 1002;
+constexpr int kPartialBufs = 4;
+constexpr int kPartialStride = 2;   // doubles per CTA slot: [0] = partial sum, [1] = flag from CTA 0
+
+enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
+
+struct LogRec { int k, inner_shown, trstatus, endreason; double loss, gradnorm, delta; };
+
+struct DevStats {
+    int exit_code, outer_iters, tcg_iters, qy_products, n_log, aborted;
+    double primal, gradnorm, gradtol_out;
+    unsigned long long solve_ns, qy_ns, sync_ns;
+};
+
+// Everything the device code needs; passed by value as the single kernel parameter.
+struct Dev {
+    // problem
+    int N, r, n3, ldq;
+    const double* Q;           // dense padded row-major, or nullptr when bsr
+    // block-CSR operator (optional): 4x4 padded blocks (row-major within block), bdim rows used
+    const int* bsr_rowptr; const int* bsr_col; const double* bsr_val; int bsr_bdim;
+    double lam;
+    // launch geometry
+    int G, NW, KS, CB, W, cpw, NSW;
+    // state (camera-block layout, 3N*r doubles each)
+    double *Y, *Ynew, *D, *Dnew, *EG, *RG, *P, *Rr, *V, *HV, *HP;
+    double *S6;                // N*6 : sym(Y_i EG_i^T), order 00 01 02 11 12 22
+    // scale state (N doubles each, index 0 pinned)
+    double *s, *snew, *gs, *rgs, *ps, *rs, *vs, *hvs, *hps;
+    double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)
+    double *partials;          // kPartialBufs * G * kPartialStride
+    unsigned* bar;             // grid barrier counter (zeroed before each launch)
+    int* abort_flag;
+    // trust-region call parameters
+    double gradtol, ls_step, max_time;
+    const double* vdir;        // escape direction, 3N (only when ls_step != 0)
+    int replicate_stale_sr, max_outer, max_inner;
+    // I/O in the reference wire layout (3N x r column-major; s length N)
+    const double* R0; const double* s0;
+    double* R_out; double* s_out;
+    DevStats* stats; LogRec* log;
+    // standalone ops
+    double qy_alpha; const double* op_in_P; const double* op_in_ps; double op_lr;
+    double* op_out_R; double* op_out_s; double* op_out_scalar;
+};
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Q is immutable for the lifetime of a kernel: read-only path, do not allocate in L1 (keeps the operand resident).
+__device__ __forceinline__ double2 ldg_stream_v2(const double* p) {
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+
+// sum over the W lanes of a sub-warp (W power of two, sub-warps aligned): every lane gets the total
+__device__ __forceinline__ double subsum(double v, int W) {
+    for (int off = W >> 1; off >= 1; off >>= 1) v += shfl_xor_d(v, off);
+    return v;
+}
+__device__ __forceinline__ double warpsum(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += shfl_xor_d(v, off);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ per-thread context
+template <int RP, int NT>
+struct Ctx {
+    static constexpr int NWARPS = NT / 32;
+    const Dev& d;
+    int tid, lane, warp, W, cpw, sw, j, slot, NSW;
+    bool act;                   // lane holds a real column (j < r)
+    int cam_lo, cam_hi;         // cameras owned by this CTA
+    unsigned epoch;             // grid barrier epoch (thread 0)
+    int pbuf;                   // rotating partial buffer
+    bool aborted;
+    unsigned long long t_qy, t_sync;   // accumulated by CTA 0 thread 0
+    double *Y, *Ynew, *s, *snew, *D, *Dnew;   // swappable state pointers (accepted steps swap instead of copying)
+    double* red;                // smem [NWARPS][3][RP]
+    double* bsum;               // smem [NWARPS]
+    double* bcast;              // smem [4]
+
+    __device__ Ctx(const Dev& dd, double* red_, double* bsum_, double* bcast_) : d(dd) {
+        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+        W = d.W; cpw = d.cpw; sw = lane / W; j = lane % W; NSW = d.NSW;
+        slot = warp * cpw + sw;
+        act = j < d.r;
+        cam_lo = (int)(((long long)blockIdx.x * d.N) / d.G);
+        cam_hi = (int)(((long long)(blockIdx.x + 1) * d.N) / d.G);
+        epoch = 0; pbuf = 0; aborted = false; t_qy = 0; t_sync = 0;
+        red = red_; bsum = bsum_; bcast = bcast_;
+        Y = d.Y; Ynew = d.Ynew; s = d.s; snew = d.snew; D = d.D; Dnew = d.Dnew;
+    }
+
+    // ---- grid-wide barrier (all CTAs co-resident: cooperative launch).  Returns false if it timed out / aborted.
+    __device__ bool grid_sync() {
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t0 = gtimer();
+            epoch += 1;
+            const unsigned target = epoch * (unsigned)d.G;
+            __threadfence();
+            atomicAdd(d.bar, 1u);
+            int ok = 1;
+            unsigned spins = 0;
+            while (ld_acquire_u32(d.bar) < target) {
+                if ((++spins & 0x3ffu) == 0) {
+                    if (*(volatile int*)d.abort_flag) { ok = 0; break; }
+                    if (gtimer() - t0 > 4000000000ull) { *(volatile int*)d.abort_flag = 1; ok = 0; break; }
+                }
+            }
+            __threadfence();
+            t_sync += gtimer() - t0;
+            bcast[3] = ok ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (bcast[3] == 0.0) { aborted = true; return false; }
+        return true;
+    }
+
+    // ---- block reduction of one double per thread -> partials[pbuf][cta]; flag travels in slot [1] (CTA 0's counts)
+    __device__ void publish(double v, double flag = 0.0) {
+        v = warpsum(v);
+        if (lane == 0) bsum[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NWARPS; ++w) t += bsum[w];
+            double* slotp = d.partials + ((size_t)pbuf * d.G + blockIdx.x) * kPartialStride;
+            slotp[0] = t; slotp[1] = flag;
+        }
+        // the following grid_sync() starts with __syncthreads and fences thread 0's stores
+    }
+    // after grid_sync: every CTA sums the G partials in the same order -> identical bits everywhere
+    __device__ double collect(double* flag_out = nullptr) {
+        if (warp == 0) {
+            const double* base = d.partials + (size_t)pbuf * d.G * kPartialStride;
+            double t = 0.0;
+            for (int c = lane; c < d.G; c += 32) t += __ldcg(base + (size_t)c * kPartialStride);
+            t = warpsum(t);
+            if (lane == 0) { bcast[0] = t; bcast[1] = __ldcg(base + 1); }
+        }
+        __syncthreads();
+        double t = bcast[0];
+        if (flag_out) *flag_out = bcast[1];
+        __syncthreads();
+        pbuf = (pbuf + 1) % kPartialBufs;
+        return t;
+    }
+};
+
+// load / store column j of camera i's 3 x r block
+__device__ __forceinline__ void ld3(const double* A, int i, int r, int j, bool act, double (&x)[3]) {
+    if (act) {
+        const double* p = A + (size_t)(3 * i) * r + j;
+        x[0] = p[0]; x[1] = p[r]; x[2] = p[2 * r];
+    } else { x[0] = x[1] = x[2] = 0.0; }
+}
+__device__ __forceinline__ void st3(double* A, int i, int r, int j, bool act, const double (&x)[3]) {
+    if (act) {
+        double* p = A + (size_t)(3 * i) * r + j;
+        p[0] = x[0]; p[r] = x[1]; p[2 * r] = x[2];
+    }
+}
+// operand store (j-major, padded ld)
+__device__ __forceinline__ void st_operand(double* Xt, int ldq, int i, int j, bool act, const double (&x)[3]) {
+    if (act) {
+        double* p = Xt + (size_t)j * ldq + 3 * i;
+        p[0] = x[0]; p[1] = x[1]; p[2] = x[2];
+    }
+}
+// symmetric 3x3 (00 01 02 11 12 22) times vector
+__device__ __forceinline__ void symv(const double (&S)[6], const double (&x)[3], double (&y)[3]) {
+    y[0] = S[0] * x[0] + S[1] * x[1] + S[2] * x[2];
+    y[1] = S[1] * x[0] + S[3] * x[1] + S[4] * x[2];
+    y[2] = S[2] * x[0] + S[4] * x[1] + S[5] * x[2];
+}
+// S = sym(A B^T) summed over the sub-warp's columns: S_ab = 1/2 sum_j (A_a B_b + A_b B_a)
+__device__ __forceinline__ void sym_outer(const double (&A)[3], const double (&B)[3], int W, double (&S)[6]) {
+    S[0] = subsum(A[0] * B[0], W);
+    S[1] = subsum(0.5 * (A[0] * B[1] + A[1] * B[0]), W);
+    S[2] = subsum(0.5 * (A[0] * B[2] + A[2] * B[0]), W);
+    S[3] = subsum(A[1] * B[1], W);
+    S[4] = subsum(0.5 * (A[1] * B[2] + A[2] * B[1]), W);
+    S[5] = subsum(A[2] * B[2], W);
+}
+// Dense/batchedQR.h:42-67 — modified Gram-Schmidt over the 3 rows (normalise row i, then remove it from rows > i)
+__device__ __forceinline__ void mgs3(double (&a)[3], int W) {
+    double n0 = sqrt(subsum(a[0] * a[0], W));
+    a[0] = a[0] / n0;
+    double d01 = subsum(a[0] * a[1], W);
+    a[1] -= d01 * a[0];
+    double d02 = subsum(a[0] * a[2], W);
+    a[2] -= d02 * a[0];
+    double n1 = sqrt(subsum(a[1] * a[1], W));
+    a[1] = a[1] / n1;
+    double d12 = subsum(a[1] * a[2], W);
+    a[2] -= d12 * a[1];
+    double n2 = sqrt(subsum(a[2] * a[2], W));
+    a[2] = a[2] / n2;
+}
+
+// ------------------------------------------------------------------------------------------------ Q.Y sweeps
+// Dense: one warp streams the 3 rows of camera `cam` over columns [kbeg,kend) (multiples of 64).  Each lane owns two
+// adjacent columns per 64-wide step: Q via 16-byte streaming loads (no L1 allocation), operand via L1.
+template <int RP>
+__device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, int kend, int lane, double (&acc)[3][RP]) {
+    const int r = d.r;
+    const size_t ldq = (size_t)d.ldq;
+    const double* q0p = d.Q + (size_t)(3 * cam) * ldq;
+    const double* xt = d.Xt;
+#pragma unroll 4
+    for (int k = kbeg + 2 * lane; k < kend; k += 64) {
+        const double2 q0 = ldg_stream_v2(q0p + k);
+        const double2 q1 = ldg_stream_v2(q0p + ldq + k);
+        const double2 q2 = ldg_stream_v2(q0p + 2 * ldq + k);
+#pragma unroll
+        for (int jj = 0; jj < RP; ++jj) {
+            if (jj < r) {
+                const double2 x = *reinterpret_cast<const double2*>(xt + (size_t)jj * ldq + k);
+                acc[0][jj] = fma(q0.x, x.x, acc[0][jj]); acc[0][jj] = fma(q0.y, x.y, acc[0][jj]);
+                acc[1][jj] = fma(q1.x, x.x, acc[1][jj]); acc[1][jj] = fma(q1.y, x.y, acc[1][jj]);
+                acc[2][jj] = fma(q2.x, x.x, acc[2][jj]); acc[2][jj] = fma(q2.y, x.y, acc[2][jj]);
+            }
+        }
+    }
+}
+
+// Block-CSR: one warp per block row (camera); lanes stride over the row's blocks.  Blocks are stored 4x4 row-major
+// (128 B, one coalesced line per block); operand rows gathered through L1/L2.  bdim==3: rows/cols 3 unused (zero).
+template <int RP>
+__device__ __forceinline__ void qy_sweep_bsr(const Dev& d, int cam, int part, int nparts, int lane, double (&acc)[3][RP]) {
+    const int r = d.r;
+    const size_t ldq = (size_t)d.ldq;
+    const int b0 = d.bsr_rowptr[cam], b1 = d.bsr_rowptr[cam + 1];
+    const double* xt = d.Xt;
+    for (int b = b0 + part * 32 + lane; b < b1; b += 32 * nparts) {
+        const int c = d.bsr_col[b];
+        const double* blk = d.bsr_val + (size_t)b * 16;
+        double q[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double2 u = ldg_stream_v2(blk + 4 * a);
+            const double2 w = ldg_stream_v2(blk + 4 * a + 2);
+            q[a][0] = u.x; q[a][1] = u.y; q[a][2] = w.x;
+        }
+#pragma unroll
+        for (int jj = 0; jj < RP; ++jj) {
+            if (jj < r) {
+                const double* xp = xt + (size_t)jj * ldq + 3 * c;
+                const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    acc[a][jj] = fma(q[a][0], x0, acc[a][jj]);
+                    acc[a][jj] = fma(q[a][1], x1, acc[a][jj]);
+                    acc[a][jj] = fma(q[a][2], x2, acc[a][jj]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ per-camera epilogues
+struct ObjArgs { const double* Ycur; const double* scur; double* Dout; };
+
+// MODE_HESS: from E_i = (Q X)_i finish ehess (trustregion.h:227-255) + ehess2rhess (:277-295); returns <P,Hp> share
+template <int RP, int NT>
+__device__ __forceinline__ double epi_hess(Ctx<RP, NT>& c, int i, const double (&E)[3], bool valid) {
+    const Dev& d = c.d;
+    const int r = d.r, W = c.W;
+    const bool act = c.act && valid;
+    double y[3], p[3], dd[3];
+    ld3(c.Y, i, r, c.j, act, y); ld3(d.P, i, r, c.j, act, p); ld3(c.D, i, r, c.j, act, dd);
+    const double si = c.s[i], psi = d.ps[i], gi = d.gs[i];
+    double S[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) S[q] = d.S6[(size_t)i * 6 + q];
+    double e[3], hr[3], t[3], sp[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { e[a] = 2.0 * E[a]; hr[a] = si * e[a] + psi * dd[a]; }
+    symv(S, p, sp);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) t[a] = hr[a] - sp[a];
+    double M[6];
+    sym_outer(y, t, W, M);
+    double hs = subsum(e[0] * y[0] + e[1] * y[1] + e[2] * y[2] + dd[0] * p[0] + dd[1] * p[1] + dd[2] * p[2], W);
+    double my[3], rhr[3];
+    symv(M, y, my);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) rhr[a] = t[a] - my[a];
+    hs += 4.0 * d.lam * (3.0 * si * si - 1.0) * psi;
+    double rhs = (i == 0) ? 0.0 : (si * si * hs + si * psi * gi);
+    st3(d.HP, i, r, c.j, act, rhr);
+    double part = act ? (p[0] * rhr[0] + p[1] * rhr[1] + p[2] * rhr[2]) : 0.0;
+    if (c.j == 0 && valid) {
+        d.hps[i] = rhs;
+        if (i > 0) part += psi * (rhs / (si * si));
+    }
+    return part;
+}
+
+// MODE_OBJ: D_i = 2 E_i ; returns camera share of  <Q sR, sR> + lam (s^2-1)^2  (trustregion.h:162-170)
+template <int RP, int NT>
+__device__ __forceinline__ double epi_obj(Ctx<RP, NT>& c, int i, const double (&E)[3], const ObjArgs& oa, bool valid) {
+    const Dev& d = c.d;
+    const bool act = c.act && valid;
+    double y[3];
+    ld3(oa.Ycur, i, d.r, c.j, act, y);
+    const double si = oa.scur[i];
+    double dn[3] = {2.0 * E[0], 2.0 * E[1], 2.0 * E[2]};
+    if (oa.Dout) st3(oa.Dout, i, d.r, c.j, act, dn);
+    double part = act ? si * (E[0] * y[0] + E[1] * y[1] + E[2] * y[2]) : 0.0;
+    if (c.j == 0 && valid && i > 0) { const double u = si * si - 1.0; part += d.lam * u * u; }
+    return part;
+}
+
+// ------------------------------------------------------------------------------------------------ fused Q.Y phase
+// Streams this CTA's cameras' rows of Q (or BSR block rows) against the operand Xt, reduces inside the CTA and runs
+// the per-camera epilogue straight from shared memory — the Q.Y result never goes to HBM in MODE_HESS / MODE_OBJ.
+template <int RP, int NT, int MODE>
+__device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa) {
+    const Dev& d = c.d;
+    const int KS = d.KS, CB = d.CB;
+    const int cslot = c.warp / KS, ks = c.warp % KS;
+    double part = 0.0;
+    unsigned long long t0 = 0;
+    if (blockIdx.x == 0 && c.tid == 0) t0 = gtimer();
+    // column range of this warp's k-split (dense): contiguous runs of 64-column steps
+    const int steps = d.ldq / 64;
+    const int kbeg = (int)(((long long)ks * steps) / KS) * 64;
+    const int kend = (int)(((long long)(ks + 1) * steps) / KS) * 64;
+    for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
+        const int cam = b0 + cslot;
+        double acc[3][RP];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
+        if (cslot < CB && cam < c.cam_hi) {
+            if (d.Q) qy_sweep_dense<RP>(d, cam, kbeg, kend, c.lane, acc);
+            else     qy_sweep_bsr<RP>(d, cam, ks, KS, c.lane, acc);
+        }
+        // warp reduction of the 3*RP partial sums (butterfly: fixed order, every lane gets the total)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int jj = 0; jj < RP; ++jj) {
+                double v = warpsum(acc[a][jj]);
+                if (c.lane == 0) c.red[(c.warp * 3 + a) * RP + jj] = v;
+            }
+        __syncthreads();
+        // epilogue: sub-warp slot q handles batch camera q
+        const int nvalid = min(CB, c.cam_hi - b0);
+        if (c.warp * c.cpw < nvalid) {                    // warp-uniform
+            const int q = c.slot;
+            const bool valid = q < nvalid;
+            const int i = valid ? (b0 + q) : b0;          // clamp: invalid sub-warps redo camera b0 without storing
+            double E[3] = {0.0, 0.0, 0.0};
+            if (c.act) {
+                for (int kk = 0; kk < KS; ++kk) {
+                    const double* rp = c.red + (size_t)((q < CB ? q : 0) * KS + kk) * 3 * RP;
+                    E[0] += rp[0 * RP + c.j]; E[1] += rp[1 * RP + c.j]; E[2] += rp[2 * RP + c.j];
+                }
+            }
+            if (MODE == MODE_OUT) {
+                if (valid && c.act) {
+                    double* o = d.op_out_R + (size_t)c.j * d.n3 + 3 * i;   // column-major 3N x r
+                    o[0] = d.qy_alpha * E[0]; o[1] = d.qy_alpha * E[1]; o[2] = d.qy_alpha * E[2];
+                }
+            } else {
+                // invalid sub-warps still take part in the shuffles; they run on camera b0 with nothing loaded/stored
+                double pv;
+                if (MODE == MODE_HESS) pv = epi_hess<RP, NT>(c, i, E, valid);
+                else                   pv = epi_obj<RP, NT>(c, i, E, oa, valid);
+                part += pv;
+            }
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && c.tid == 0) c.t_qy += gtimer() - t0;
+    return part;
+}
+
+}  // namespace xm

@@ -1,0 +1,40 @@
+// xm_host.h — internal: the handle behind the C-ABI (shared by xm_capi.cu and xm_certify.cu).
+#pragma once
+#include "../../include/xm_b200.h"
+#include "xm_device.cuh"
+#include <string>
+
+struct xm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    xm_options opt{};
+    std::string err;
+    int num_sm = 0;
+    // operator
+    int N = 0, n3 = 0, ldq = 0;
+    double* Qp = nullptr; size_t Qp_cap = 0;          // padded row-major dense Q
+    double* Qstage = nullptr; size_t Qstage_cap = 0;   // staging for the user's column-major matrix
+    int* bsr_rowptr = nullptr; int* bsr_col = nullptr; double* bsr_val = nullptr; int bsr_bdim = 0; bool is_bsr = false;
+    // workspace (one allocation, carved per (N, r))
+    char* ws = nullptr; size_t ws_cap = 0; int ws_r = -1, ws_N = -1, ws_G = -1, ws_ldq = -1;
+    xm::Dev dev{};                                         // pointer template, filled by carve()
+    // small persistent device objects
+    xm::DevStats* d_stats = nullptr; xm::LogRec* d_log = nullptr; unsigned* d_bar = nullptr; int* d_abort = nullptr;
+    double* d_scalar = nullptr;
+    // I/O staging in the wire layout (device)
+    double *io_R0 = nullptr, *io_s0 = nullptr, *io_v = nullptr, *io_Rout = nullptr, *io_sout = nullptr, *io_P = nullptr, *io_ps = nullptr;
+    size_t io_cap_R = 0, io_cap_s = 0;
+    // pinned host mirrors
+    xm::DevStats* h_stats = nullptr; xm::LogRec* h_log = nullptr;
+    int launches = 0;
+};
+
+#define XM_CUDA(h, call)                                                                           \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+            return XM_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
