@@ -120,7 +120,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     Qh, prob = make_problem()
     N = N_CAMERAS; n3 = 3 * N
-    h = capi.Handle(device=local)
+    h = capi.Handle(device=local, profile=bool(int(os.environ.get("XM_PROFILE", "0"))), qy_variant=int(os.environ.get("XM_QY_VARIANT", "0")),
+                    vec_in_global=bool(int(os.environ.get("XM_VEC_GLOBAL", "0"))))
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
     # host (pinned) and device copies of the inputs, wire layout (column-major)
@@ -183,7 +184,9 @@ def run_ours(args):
     # roofline of the dominant kernel phase: the dense Q.Y, timed alone
     X_dev = torch.randn(RANK, n3, dtype=torch.float64, device="cuda"); O_dev = torch.empty_like(X_dev)
     h.qy_dev(RANK, X_dev.data_ptr(), O_dev.data_ptr())
-    qy_ms = h.bench_qy(RANK, 50)
+    qy_ms = h.bench_qy(RANK, 50)                 # 50 products inside one launch, free-running CTAs
+    qy_ms_lockstep = h.bench_qy(RANK, -50)       # same with a grid barrier after every product (the solver's regime)
+    barrier_us = h.bench_barrier(RANK, 2000)
     alg_bytes = 72.0 * N * N + 48.0 * N * RANK
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (qy_ms * 1e-3) / 1e9
@@ -202,14 +205,17 @@ def run_ours(args):
                    "time_to_kkt_ms": ms_dev / args.steps, "final_objective": primal, "final_gradnorm": st["gradnorm"], "exit": st["exit"],
                    "l2": "inputs larger than L2 (Q = %.1f MB vs 126 MB L2)" % (alg_bytes / 1e6),
                    "grid_ctas": st["grid_ctas"], "threads_per_cta": st["threads_per_cta"], "ksplit": st["ksplit"],
-                   "in_kernel_ms": {"solve": st["solve_ms"], "qy": st["qy_ms"], "grid_sync_wait": st["sync_ms"]},
+                   "in_kernel_ms": {"solve": st["solve_ms"], "qy": st["qy_ms"], "grid_sync_wait": st["sync_ms"],
+                                    "qy_first_tile_wait": st["phase_ms"][0], "qy_tile_waits": st["phase_ms"][1], "qy_tile_math": st["phase_ms"][2],
+                                    "qy_reduce_epilogue": st["phase_ms"][3], "profile_timers_on": bool(int(os.environ.get("XM_PROFILE", "0")))},
+                   "grid_barrier_us": barrier_us,
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas of the same solve (no collective; camera-partitioned solve is a later row)"},
         "e2e": {"value": e2e_value, "unit": "tCG iterations/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(8 * (n3 * n3 + n3 * RANK + N)), "d2h_bytes_per_step": int(8 * (n3 * RANK + N))},
         "gpu_launches": int(args.steps),   # one persistent solve kernel per step (e2e adds one re-layout kernel per step)
         "roofline": {"bound": "hbm", "kernel": "xm_ops_kernel<3,512> (dense Q.Y phase, same device code as inside the solve)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "algorithmic_bytes": alg_bytes, "ms_per_launch": qy_ms, "peak_source": peak_src,
+                     "algorithmic_bytes": alg_bytes, "ms_per_launch": qy_ms, "ms_per_product_lockstep": qy_ms_lockstep, "peak_source": peak_src,
                      "solve_level": {"achieved": alg_bytes * st["qy_products"] / (st["solve_ms"] * 1e-3) / 1e9,
                                      "note": "Q.Y bytes x products / whole persistent-kernel time (includes all per-camera phases and grid syncs)"}},
         "cpu_baseline": {"value": cpu_its, "unit": "tCG iterations/s", "cores": os.cpu_count(), "kind": "port",

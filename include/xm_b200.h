@@ -61,7 +61,9 @@ typedef struct xm_options {
     int verbose;            /* 1 = print the reference's per-outer-iteration table to stdout after the solve */
     int max_outer;          /* default 1000 (trustregion.h:417) */
     int max_inner;          /* default 1000 (trustregion.h:416) */
-    int qy_variant;         /* 0 = auto; dense Q.Y kernel variant (tuning hook) */
+    int qy_variant;         /* dense Q.Y path: 0 = auto (2-D TMA ring + cross-phase prefetch), 1 = direct streaming loads */
+    int vec_in_global;      /* 1 = keep the per-camera state vectors in HBM/L2 even when they would fit in shared memory */
+    int profile;            /* 1 = fine-grained in-kernel phase timers (xm_stats.phase_ms); costs a few percent */
 } xm_options;
 
 typedef struct xm_log_rec { /* one line of the reference's stdout table (trustregion.h:487-526) */
@@ -81,6 +83,7 @@ typedef struct xm_stats {
     double qy_ms;           /* device time spent inside Q.Y sweeps (globaltimer, CTA 0) */
     double sync_ms;         /* device time CTA 0 spent waiting in grid barriers */
     int grid_ctas, threads_per_cta, ksplit, launches; /* launch configuration actually used / kernels launched */
+    double phase_ms[4];     /* CTA 0 breakdown of the Q.Y phases: first-tile wait, later tile waits, tile math, reduce+epilogue */
 } xm_stats;
 
 #define XM_LOG_CAP 1002
@@ -101,6 +104,11 @@ int  xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, const int* 
 /* out = alpha * Q * X ; X, out: 3N x r column-major (ld = 3N). */
 int  xm_qy(xm_handle* h, int r, double alpha, const double* X, double* out);
 int  xm_qy_dev(xm_handle* h, int r, double alpha, const double* X_dev, double* out_dev);
+/* Measurement hook: average device time (ms, CUDA events on the handle's stream) of `iters` back-to-back launches of
+ * the Q.Y kernel on the operand left in the workspace by the last xm_qy/xm_qy_dev call. */
+int  xm_bench_qy(xm_handle* h, int r, int iters, double* avg_ms);   /* iters < 0: grid barrier after every product */
+int  xm_bench_barrier(xm_handle* h, int r, int iters, double* avg_us);
+int  xm_debug_trace(xm_handle* h, unsigned long long* out256);   /* (tag, ns) pairs of the last profiled solve */
 
 /* Mirrors XMtrustregion.  R0/R_out: 3N x r col-major; s0/s_out: length N (s[0] = 1); v: length 3N or NULL when
  * ls_step == 0.  gradtol_inout is updated like the reference's by-reference gradtol.  stats/log may be NULL. */

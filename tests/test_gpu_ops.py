@@ -40,15 +40,32 @@ def test_qy_matches_oracle(gpu_handle_factory, N, r):
     assert rel(got, 2.0 * Q @ X) < TOL
 
 
-@pytest.mark.parametrize("grid,ks", [(1, 1), (1, 16), (3, 4), (16, 2), (148, 0), (40, 8)])
-def test_qy_launch_geometries(gpu_handle_factory, grid, ks):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("grid,ks", [(1, 1), (1, 16), (3, 4), (16, 2), (148, 0), (40, 8), (97, 15), (20, 3)])
+def test_qy_launch_geometries(gpu_handle_factory, grid, ks, variant):
+    """Both dense Q.Y paths (0: 2-D TMA ring, 1: direct streaming loads) over grid sizes / k-splits, incl. multi-batch
+    CTAs (grid=1: 97 cameras in one CTA), ring wrap-around and the OOB-filled tail chunk (3N = 291 is not a multiple of 128)."""
     rng = np.random.default_rng(7)
     N, r = 97, 5
     Q = rand_psd(3 * N, rng)
     X = rng.standard_normal((3 * N, r))
-    h = gpu_handle_factory(grid_ctas=grid, ksplit=ks)
+    h = gpu_handle_factory(grid_ctas=grid, ksplit=ks, qy_variant=variant)
     h.set_q_dense(Q)
     assert rel(h.qy(X), Q @ X) < TOL
+    assert rel(h.qy(2 * X), 2 * Q @ X) < TOL          # second call on the same handle (ring state is per launch)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_solver_paths_agree(gpu_handle_factory, variant):
+    from xm_code_b200 import problems
+    Q, _ = problems.synthetic_dense_q(200, seed=9)
+    ref = xo.trust_region(Q, xo.identity_init(200, 3), np.ones(200), 0.0, 1e-7)
+    for grid in (0, 5):                                  # 5 CTAs x 40 cameras: multi-batch, prefetch across batches
+        h = gpu_handle_factory(qy_variant=variant, grid_ctas=grid)
+        h.set_q_dense(Q)
+        got = h.trust_region(xo.from_blocks(xo.identity_init(200, 3)), np.ones(200), 0.0, 1e-7)
+        assert abs(got.primal - ref.primal) <= 1e-9 * abs(ref.primal)
+        assert np.max(np.abs(got.s - ref.s)) < 1e-6
 
 
 def test_qy_strided_ld_and_reupload(gpu_handle_factory):

@@ -21,7 +21,8 @@ EXIT_CODES = {1: "gradtol", 2: "rdotr_tiny", 3: "maxtime", 4: "model_increase", 
 
 class XmOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("grid_ctas", C.c_int), ("ksplit", C.c_int), ("replicate_stale_sr", C.c_int),
-                ("verbose", C.c_int), ("max_outer", C.c_int), ("max_inner", C.c_int), ("qy_variant", C.c_int)]
+                ("verbose", C.c_int), ("max_outer", C.c_int), ("max_inner", C.c_int), ("qy_variant", C.c_int),
+                ("vec_in_global", C.c_int), ("profile", C.c_int)]
 
 
 class XmLogRec(C.Structure):
@@ -33,13 +34,14 @@ class XmStats(C.Structure):
     _fields_ = [("exit_code", C.c_int), ("outer_iters", C.c_int), ("tcg_iters", C.c_int), ("qy_products", C.c_int),
                 ("n_log", C.c_int), ("primal", C.c_double), ("gradnorm", C.c_double), ("solve_ms", C.c_double),
                 ("qy_ms", C.c_double), ("sync_ms", C.c_double), ("grid_ctas", C.c_int), ("threads_per_cta", C.c_int),
-                ("ksplit", C.c_int), ("launches", C.c_int)]
+                ("ksplit", C.c_int), ("launches", C.c_int), ("phase_ms", C.c_double * 4)]
 
 
 EXPORTS = [
     "xm_default_options", "xm_create", "xm_destroy", "xm_last_error", "xm_set_stream", "xm_set_q_dense",
     "xm_set_q_dense_dev", "xm_set_q_bsr", "xm_qy", "xm_qy_dev", "xm_trust_region", "xm_trust_region_dev",
     "xm_op_objective", "xm_op_rgrad", "xm_op_rhess", "xm_op_retract", "xm_certify", "xm_escape_scale", "xm_bench_qy",
+    "xm_bench_barrier", "xm_debug_trace",
 ]
 
 _lib = None
@@ -79,6 +81,8 @@ def load(path: str | None = None):
     lib.xm_certify.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, dp, dp, dp, C.POINTER(C.c_int)]
     lib.xm_escape_scale.argtypes = [C.c_int, vp, vp]
     lib.xm_bench_qy.argtypes = [vp, C.c_int, C.c_int, dp]
+    lib.xm_bench_barrier.argtypes = [vp, C.c_int, C.c_int, dp]
+    lib.xm_debug_trace.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("xm_default_options", "xm_last_error"):
@@ -114,13 +118,15 @@ class Handle:
     """One xm_handle (one CUDA device)."""
 
     def __init__(self, device: int = 0, grid_ctas: int = 0, ksplit: int = 0, replicate_stale_sr: bool = True,
-                 verbose: bool = False, max_outer: int = 1000, max_inner: int = 1000):
+                 verbose: bool = False, max_outer: int = 1000, max_inner: int = 1000, qy_variant: int = 0,
+                 vec_in_global: bool = False, profile: bool = False):
         self.lib = load()
         opt = XmOptions()
         self.lib.xm_default_options(C.byref(opt))
         opt.device = device; opt.grid_ctas = grid_ctas; opt.ksplit = ksplit
         opt.replicate_stale_sr = int(replicate_stale_sr); opt.verbose = int(verbose)
-        opt.max_outer = max_outer; opt.max_inner = max_inner
+        opt.max_outer = max_outer; opt.max_inner = max_inner; opt.qy_variant = qy_variant
+        opt.vec_in_global = int(vec_in_global); opt.profile = int(profile)
         self._h = C.c_void_p()
         rc = self.lib.xm_create(C.byref(self._h), C.byref(opt))
         if rc != 0:
@@ -184,6 +190,17 @@ class Handle:
         self._check(self.lib.xm_bench_qy(self._h, r, iters, C.byref(ms)), "xm_bench_qy")
         return ms.value
 
+    def debug_trace(self):
+        buf = (C.c_ulonglong * 256)()
+        self._check(self.lib.xm_debug_trace(self._h, C.cast(buf, C.c_void_p)), "xm_debug_trace")
+        out = [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(128) if buf[2 * i + 1]]
+        return out
+
+    def bench_barrier(self, r: int, iters: int) -> float:
+        us = C.c_double()
+        self._check(self.lib.xm_bench_barrier(self._h, r, iters, C.byref(us)), "xm_bench_barrier")
+        return us.value
+
     def objective(self, R, s, lam=0.0) -> float:
         R = _f64(R); s = _f64(s)
         f = C.c_double()
@@ -223,6 +240,7 @@ class Handle:
                                       C.byref(primal), C.byref(st), C.cast(log, C.c_void_p))
         self._check(rc, "xm_trust_region")
         stats = {f[0]: getattr(st, f[0]) for f in XmStats._fields_}
+        stats["phase_ms"] = list(st.phase_ms)
         stats["exit"] = EXIT_CODES.get(st.exit_code, str(st.exit_code))
         lg = [(log[i].k, log[i].inner_shown, log[i].loss, log[i].gradnorm, log[i].trstatus, log[i].endreason, log[i].delta)
               for i in range(st.n_log)]
@@ -236,6 +254,7 @@ class Handle:
                                           C.byref(primal), C.byref(st), None)
         self._check(rc, "xm_trust_region_dev")
         stats = {f[0]: getattr(st, f[0]) for f in XmStats._fields_}
+        stats["phase_ms"] = list(st.phase_ms)
         stats["exit"] = EXIT_CODES.get(st.exit_code, str(st.exit_code))
         return primal.value, gt.value, stats
 

@@ -12,6 +12,25 @@
 
 using namespace xm;
 
+namespace xm {
+// ------------------------------------------------------------------------------------------------ layout kernels
+// Qp[i*ldq + k] = Qcm[i + ld*k]  (column-major user matrix -> padded row-major), 32x32 smem tiles, pad stays zero
+__global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld, int n3, double* __restrict__ Qp, int ldq) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y * 32, bk = blockIdx.x * 32;
+    for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // read: consecutive threads along i (contiguous in col-major)
+        const int k = bk + t, i = bi + threadIdx.x;
+        tile[t][threadIdx.x] = (i < n3 && k < n3) ? Qcm[(size_t)i + (size_t)ld * k] : 0.0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // write: consecutive threads along k
+        const int i = bi + t, k = bk + threadIdx.x;
+        if (i < n3 && k < ldq) Qp[(size_t)i * ldq + k] = (k < n3) ? tile[threadIdx.x][t] : 0.0;
+    }
+}
+
+}  // namespace xm
+
 static_assert(sizeof(xm_log_rec) == sizeof(LogRec), "log record layout");
 static_assert(XM_LOG_CAP == kLogCap, "log cap");
 static_assert(XM_MAX_RANK == kMaxRank, "max rank");
@@ -20,7 +39,7 @@ extern "C" void xm_default_options(xm_options* o) {
     if (!o) return;
     memset(o, 0, sizeof(*o));
     o->device = 0; o->grid_ctas = 0; o->ksplit = 0; o->replicate_stale_sr = 1; o->verbose = 0;
-    o->max_outer = 1000; o->max_inner = 1000; o->qy_variant = 0;
+    o->max_outer = 1000; o->max_inner = 1000; o->qy_variant = 0; o->vec_in_global = 0; o->profile = 0;
 }
 
 extern "C" const char* xm_last_error(const xm_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -42,6 +61,12 @@ extern "C" int xm_create(xm_handle** out, const xm_options* opt) {
         delete h; return XM_ENOGPU;      // kernels are built for sm_100a only
     }
     h->num_sm = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    {
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->encode_tiled, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); h->encode_tiled = nullptr; }
+    }
     if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return XM_ECUDA; }
     bool ok = cudaMalloc(&h->d_stats, sizeof(DevStats)) == cudaSuccess &&
               cudaMalloc(&h->d_log, sizeof(LogRec) * kLogCap) == cudaSuccess &&
@@ -129,7 +154,7 @@ extern "C" int xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, c
 }
 
 // ------------------------------------------------------------------------------------------------ launch planning
-struct Plan { int RP, NT, NW, W, cpw, NSW, G, KS, CB; };
+struct Plan { int RP, NT, NW, W, cpw, NSW, G, KS, CB; int use_tma, KC, ST, nbmax, nchunks, stage_doubles; int box_nb[3]; size_t dyn_smem; int vec_smem, cpc; size_t vec_bytes; int nprod, NWC; };
 
 static int rank_pad(int r) {
     static const int pads[] = {3, 4, 5, 6, 8, 10, 12, 16, 20};
@@ -137,7 +162,22 @@ static int rank_pad(int r) {
     return -1;
 }
 
-static Plan make_plan(const xm_handle* h, int r) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D FP64 tensor map over a row-major [rows x cols] array with row pitch `pitch` elements; box = [box_rows x box_cols]
+static int make_map(xm_handle* h, CUtensorMap* m, const double* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols, uint32_t box_rows) {
+    if (!h->encode_tiled) { h->err = "cuTensorMapEncodeTiled unavailable"; return XM_ECUDA; }
+    cuuint64_t dims[2] = {cols, rows}; cuuint64_t strides[1] = {pitch * sizeof(double)};
+    cuuint32_t box[2] = {box_cols, box_rows}; cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return XM_ECUDA; }
+    return XM_OK;
+}
+
+static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     Plan p{};
     p.RP = rank_pad(r);
     p.NT = (p.RP <= 10) ? 512 : 256;
@@ -150,14 +190,43 @@ static Plan make_plan(const xm_handle* h, int r) {
     G = std::max(1, std::min(G, h->N));
     p.G = G;
     const int cpc = (h->N + G - 1) / G;
+    p.use_tma = (allow_tma && !h->is_bsr && h->opt.qy_variant != 1 && h->encode_tiled) ? 1 : 0;
+    p.nprod = p.use_tma ? 1 : 0;                        // TMA path: the last nprod warps are producers (1 suffices)
+    if (const char* e = getenv("XM_TUNE_NPROD")) { int v = atoi(e); if (p.use_tma && v >= 1 && v <= 4) p.nprod = v; }     // tuning hook
+    const int nwork = p.NW - p.nprod;                   // warps that stream
+    p.NWC = nwork;
+    p.KC = 192;     // measured (profiles/r01_sweep_ring*.txt): fewer, larger chunks win; 192 keeps >= 3 stages for r <= 8
+    if (const char* e = getenv("XM_TUNE_KC")) { int v = atoi(e); if (v >= 64 && v <= 256 && v % 64 == 0) p.KC = v; }   // tuning hook
+    if (allow_tma == 2) p.KC = 128;
+    p.nchunks = (h->ldq + p.KC - 1) / p.KC;
+    // k-split: the largest divisor KS of nwork with KS * cpc <= nwork (or the caller's cap), at most one chunk/step each
+    const int kmax = p.use_tma ? p.nchunks : (h->is_bsr ? nwork : std::max(1, h->ldq / 64));
     int KS = 1;
-    if (h->opt.ksplit > 0) KS = h->opt.ksplit;
-    else while (KS * 2 * cpc <= p.NW) KS *= 2;
-    KS = std::max(1, std::min(KS, p.NW));
-    while (p.NW % KS) KS--;
-    if (!h->is_bsr) KS = std::max(1, std::min(KS, h->ldq / 64));
-    while (p.NW % KS) KS--;
-    p.KS = KS; p.CB = p.NW / KS;
+    for (int k = 1; k <= nwork; ++k)
+        if (nwork % k == 0 && k <= kmax && ((h->opt.ksplit > 0) ? (k <= h->opt.ksplit) : (k * cpc <= nwork))) KS = k;
+    p.KS = KS; p.CB = nwork / KS;
+    p.cpc = cpc;
+    // per-CTA state vectors in shared memory when they are small (kills the L2 round trips of every per-camera phase)
+    size_t budget = (size_t)std::min(h->smem_optin, 227 * 1024) - 12 * 1024;               // static smem + slack
+    p.vec_bytes = (((size_t)(kNumVecR * 3 * r + kNumVecS + 6) * cpc * sizeof(double)) + 127) / 128 * 128;
+    p.vec_smem = (h->opt.vec_in_global == 0 && p.vec_bytes <= 64 * 1024) ? 1 : 0;
+    if (p.vec_smem) budget -= p.vec_bytes;
+    p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
+    if (p.use_tma) {
+        p.nbmax = std::min(p.CB, cpc);
+        p.stage_doubles = (3 * p.nbmax + r) * p.KC;
+        int ST = (int)((budget - 1024) / ((size_t)p.stage_doubles * sizeof(double)));
+        ST = std::min(ST, 24);
+        if (const char* e = getenv("XM_TUNE_ST")) { int v = atoi(e); if (v >= 2) ST = std::min(ST, v); }                      // tuning hook
+        if (ST < 3 && p.KC > 128) return make_plan(h, r, 2);   // deep ring matters more than chunk width: retry with KC = 128
+        if (ST < 2) return make_plan(h, r, 0);          // ring does not fit: direct streaming loads
+        p.ST = ST;
+        // batch heights that occur: CTAs own q or q+1 cameras; full batches have CB cameras, a CTA's last batch the rest
+        auto last = [&](int n) { return n <= 0 ? p.CB : n - ((n - 1) / p.CB) * p.CB; };
+        const int q = h->N / G;
+        p.box_nb[0] = std::min(p.CB, cpc); p.box_nb[1] = last(q); p.box_nb[2] = last(q + 1);
+        p.dyn_smem += (size_t)ST * p.stage_doubles * sizeof(double) + 3 * ST * sizeof(unsigned long long);
+    }
     return p;
 }
 
@@ -167,7 +236,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int carve(xm_handle* h, int r, const Plan& p) {
     const size_t N = h->N, n3 = h->n3, ldq = h->ldq;
     const size_t vecR = align_up(n3 * r * sizeof(double), 256), vecS = align_up(N * sizeof(double), 256);
-    const size_t total = 11 * vecR + align_up(N * 6 * sizeof(double), 256) + 9 * vecS + align_up((size_t)r * ldq * sizeof(double), 256) +
+    const size_t total = kNumVecR * vecR + align_up(N * 6 * sizeof(double), 256) + kNumVecS * vecS + align_up((size_t)r * ldq * sizeof(double), 256) +
                          align_up((size_t)kPartialBufs * p.G * kPartialStride * sizeof(double), 256);
     bool fresh = false;
     if (h->ws_cap < total) {
@@ -181,23 +250,32 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         h->ws_r = r; h->ws_N = (int)N; h->ws_G = p.G; h->ws_ldq = (int)ldq;
     }
     char* q = h->ws;
-    auto takeR = [&]() { double* t = (double*)q; q += vecR; return t; };
-    auto takeS = [&]() { double* t = (double*)q; q += vecS; return t; };
     Dev& d = h->dev;
     d = Dev{};
-    d.Y = takeR(); d.Ynew = takeR(); d.D = takeR(); d.Dnew = takeR(); d.EG = takeR(); d.RG = takeR(); d.P = takeR();
-    d.Rr = takeR(); d.V = takeR(); d.HV = takeR(); d.HP = takeR();
+    d.rbase = (double*)q; d.rstride = (long long)(vecR / sizeof(double)); q += kNumVecR * vecR;
     d.S6 = (double*)q; q += align_up(N * 6 * sizeof(double), 256);
-    d.s = takeS(); d.snew = takeS(); d.gs = takeS(); d.rgs = takeS(); d.ps = takeS(); d.rs = takeS(); d.vs = takeS();
-    d.hvs = takeS(); d.hps = takeS();
+    d.sbase = (double*)q; d.sstride = (long long)(vecS / sizeof(double)); q += kNumVecS * vecS;
     d.Xt = (double*)q; q += align_up((size_t)r * ldq * sizeof(double), 256);
     d.partials = (double*)q;
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
     d.Q = h->is_bsr ? nullptr : h->Qp;
     d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim;
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;
+    d.vec_smem = p.vec_smem; d.cpc_max = p.cpc; d.profile = h->opt.profile;
+    d.nprod = p.nprod; d.NWC = p.NWC;
+    d.use_tma = p.use_tma; d.KC = p.KC; d.ST = p.ST; d.nbmax = p.nbmax; d.nchunks = p.nchunks; d.stage_doubles = p.stage_doubles;
+    if (p.use_tma) {
+        int rc = make_map(h, &h->mapX, d.Xt, (uint64_t)ldq, (uint64_t)r, (uint64_t)ldq, (uint32_t)p.KC, (uint32_t)r);
+        if (rc) return rc;
+        for (int t = 0; t < 3; ++t) {
+            rc = make_map(h, &h->mapQ[t], h->Qp, (uint64_t)ldq, (uint64_t)n3, (uint64_t)ldq, (uint32_t)p.KC, (uint32_t)(3 * p.box_nb[t]));
+            if (rc) return rc;
+            d.box_nb[t] = p.box_nb[t];
+        }
+    }
     d.bar = h->d_bar; d.abort_flag = h->d_abort; d.stats = h->d_stats; d.log = h->d_log;
     d.op_out_scalar = h->d_scalar;
+    d.op_repeat = 1;
     d.replicate_stale_sr = h->opt.replicate_stale_sr; d.max_outer = h->opt.max_outer; d.max_inner = h->opt.max_inner;
     return XM_OK;
 }
@@ -220,40 +298,18 @@ static int ensure_io(xm_handle* h, int r) {
     return XM_OK;
 }
 
-template <int RP, int NT>
-static cudaError_t launch_solve_t(const Dev& d, cudaStream_t st) {
-    void* args[] = {(void*)&d};
-    return cudaLaunchCooperativeKernel((const void*)xm_solve_kernel<RP, NT>, dim3(d.G), dim3(NT), args, 0, st);
-}
-template <int RP, int NT>
-static cudaError_t launch_ops_t(const Dev& d, int opcode, cudaStream_t st) {
-    void* args[] = {(void*)&d, (void*)&opcode};
-    return cudaLaunchCooperativeKernel((const void*)xm_ops_kernel<RP, NT>, dim3(d.G), dim3(NT), args, 0, st);
-}
-#define XM_DISPATCH(RPV, CALL512, CALL256)                                   \
-    switch (RPV) {                                                           \
-        case 3:  { constexpr int RP = 3;  constexpr int NT = 512; CALL512; } break;  \
-        case 4:  { constexpr int RP = 4;  constexpr int NT = 512; CALL512; } break;  \
-        case 5:  { constexpr int RP = 5;  constexpr int NT = 512; CALL512; } break;  \
-        case 6:  { constexpr int RP = 6;  constexpr int NT = 512; CALL512; } break;  \
-        case 8:  { constexpr int RP = 8;  constexpr int NT = 512; CALL512; } break;  \
-        case 10: { constexpr int RP = 10; constexpr int NT = 512; CALL512; } break;  \
-        case 12: { constexpr int RP = 12; constexpr int NT = 256; CALL256; } break;  \
-        case 16: { constexpr int RP = 16; constexpr int NT = 256; CALL256; } break;  \
-        case 20: { constexpr int RP = 20; constexpr int NT = 256; CALL256; } break;  \
-        default: e = cudaErrorInvalidValue;                                  \
-    }
+// Kernel instantiations live in xm_inst.cu, compiled three times (groups of padded ranks) so the build parallelises.
+cudaError_t xm_launch_group0(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st);   // RP 3,4,5
+cudaError_t xm_launch_group1(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st);   // RP 6,8,10
+cudaError_t xm_launch_group2(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st);   // RP 12,16,20
 
-static cudaError_t launch_solve(const Dev& d, int RPV, cudaStream_t st) {
-    cudaError_t e = cudaSuccess;
-    XM_DISPATCH(RPV, e = (launch_solve_t<RP, NT>(d, st)), e = (launch_solve_t<RP, NT>(d, st)));
-    return e;
+static cudaError_t launch_any(int kind, const xm_handle* h, const Dev& d, int opcode, const Plan& p, cudaStream_t st) {
+    if (p.RP <= 5) return xm_launch_group0(kind, p.RP, h, d, opcode, p.dyn_smem, st);
+    if (p.RP <= 10) return xm_launch_group1(kind, p.RP, h, d, opcode, p.dyn_smem, st);
+    return xm_launch_group2(kind, p.RP, h, d, opcode, p.dyn_smem, st);
 }
-static cudaError_t launch_ops(const Dev& d, int opcode, int RPV, cudaStream_t st) {
-    cudaError_t e = cudaSuccess;
-    XM_DISPATCH(RPV, e = (launch_ops_t<RP, NT>(d, opcode, st)), e = (launch_ops_t<RP, NT>(d, opcode, st)));
-    return e;
-}
+static cudaError_t launch_solve(const xm_handle* h, const Dev& d, const Plan& p, cudaStream_t st) { return launch_any(0, h, d, 0, p, st); }
+static cudaError_t launch_ops(const xm_handle* h, const Dev& d, int opcode, const Plan& p, cudaStream_t st) { return launch_any(1, h, d, opcode, p, st); }
 
 static int prepare(xm_handle* h, int r, Plan* plan) {
     if (!h) return XM_EINVAL;
@@ -291,7 +347,7 @@ static int qy_common(xm_handle* h, int r, double alpha, const double* X, double*
                                  (size_t)d.n3 * sizeof(double), r, kin, h->stream));
     d.qy_alpha = alpha;
     d.op_out_R = dev_ptrs ? out : h->io_Rout;
-    XM_CUDA(h, launch_ops(d, 0, p.RP, h->stream));
+    XM_CUDA(h, launch_ops(h, d, 0, p, h->stream));
     h->launches++;
     if (!dev_ptrs) {
         XM_CUDA(h, cudaMemcpyAsync(out, h->io_Rout, (size_t)d.n3 * r * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -308,22 +364,49 @@ extern "C" int xm_bench_qy(xm_handle* h, int r, int iters, double* avg_ms) {
     Plan p;
     int rc = prepare(h, r, &p);
     if (rc) return rc;
-    if (!avg_ms || iters <= 0) return XM_EINVAL;
+    if (!avg_ms || iters == 0) return XM_EINVAL;
     Dev d = h->dev;
     d.qy_alpha = 1.0; d.op_out_R = h->io_Rout;
     cudaEvent_t e0, e1;
     XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
-    for (int w = 0; w < 3; ++w) XM_CUDA(h, launch_ops(d, 0, p.RP, h->stream));
+    // iters > 0: `iters` products inside ONE launch (steady state, ring prefetch across products, like the solver);
+    d.op_repeat = iters;        // negative: |iters| products with a grid barrier after each (the solver's lock-step)
+    if (iters < 0) iters = -iters;
+    XM_CUDA(h, launch_ops(h, d, 0, p, h->stream));            // warm-up launch
     XM_CUDA(h, cudaEventRecord(e0, h->stream));
-    for (int it = 0; it < iters; ++it) XM_CUDA(h, launch_ops(d, 0, p.RP, h->stream));
+    XM_CUDA(h, launch_ops(h, d, 0, p, h->stream));
     XM_CUDA(h, cudaEventRecord(e1, h->stream));
     XM_CUDA(h, cudaEventSynchronize(e1));
     float ms = 0;
     XM_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    h->launches += iters + 3;
+    h->launches += 2;
     *avg_ms = (double)ms / iters;
     return XM_OK;
+}
+
+// measurement hook: average device time (us) of one grid barrier of the persistent kernel (|iters| barriers, one launch)
+extern "C" int xm_bench_barrier(xm_handle* h, int r, int iters, double* avg_us) {
+    Plan p;
+    int rc = prepare(h, r, &p);
+    if (rc) return rc;
+    if (!avg_us || iters <= 0) return XM_EINVAL;
+    Dev d = h->dev;
+    d.op_repeat = iters;
+    cudaEvent_t e0, e1;
+    XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
+    XM_CUDA(h, launch_ops(h, d, 5, p, h->stream));
+    XM_CUDA(h, cudaMemsetAsync(h->d_bar, 0, 256, h->stream));
+    XM_CUDA(h, cudaEventRecord(e0, h->stream));
+    XM_CUDA(h, launch_ops(h, d, 5, p, h->stream));
+    XM_CUDA(h, cudaEventRecord(e1, h->stream));
+    XM_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0;
+    XM_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h->launches += 2;
+    *avg_us = (double)ms * 1e3 / iters;
+    return check_abort(h);
 }
 
 // ------------------------------------------------------------------------------------------------ trust region
@@ -382,7 +465,7 @@ static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, do
     cudaEvent_t e0, e1;
     XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
     XM_CUDA(h, cudaEventRecord(e0, h->stream));
-    XM_CUDA(h, launch_solve(d, p.RP, h->stream));
+    XM_CUDA(h, launch_solve(h, d, p, h->stream));
     XM_CUDA(h, cudaEventRecord(e1, h->stream));
     h->launches++;
     if (!dev_ptrs) {
@@ -406,6 +489,7 @@ static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, do
         stats->qy_products = S.qy_products; stats->n_log = S.n_log; stats->primal = S.primal; stats->gradnorm = S.gradnorm;
         stats->solve_ms = ms; stats->qy_ms = S.qy_ns * 1e-6; stats->sync_ms = S.sync_ns * 1e-6;
         stats->grid_ctas = p.G; stats->threads_per_cta = p.NT; stats->ksplit = p.KS; stats->launches = 1;
+        for (int q = 0; q < 4; ++q) stats->phase_ms[q] = S.dbg[q] * 1e-6;
     }
     if (log) memcpy(log, h->h_log, sizeof(LogRec) * (size_t)S.n_log);
     if (h->opt.verbose) print_log(S, h->h_log);
@@ -438,7 +522,7 @@ static int op_common(xm_handle* h, int r, int opcode, const double* R, const dou
     if (ps) XM_CUDA(h, cudaMemcpyAsync(h->io_ps, ps, bS, cudaMemcpyHostToDevice, h->stream));
     d.R0 = h->io_R0; d.s0 = h->io_s0; d.op_in_P = h->io_P; d.op_in_ps = h->io_ps; d.op_lr = lr; d.lam = lam;
     d.op_out_R = h->io_Rout; d.op_out_s = h->io_sout;
-    XM_CUDA(h, launch_ops(d, opcode, p.RP, h->stream));
+    XM_CUDA(h, launch_ops(h, d, opcode, p, h->stream));
     h->launches++;
     if (outR) XM_CUDA(h, cudaMemcpyAsync(outR, h->io_Rout, bR, cudaMemcpyDeviceToHost, h->stream));
     if (outS) XM_CUDA(h, cudaMemcpyAsync(outS, h->io_sout, bS, cudaMemcpyDeviceToHost, h->stream));
@@ -461,6 +545,13 @@ extern "C" int xm_op_retract(xm_handle* h, int r, const double* R, const double*
                              double lr, double* Rn, double* sn) {
     if (!etaR || !etas) return XM_EINVAL;
     return op_common(h, r, 4, R, s, 0.0, etaR, etas, lr, Rn, sn, nullptr);
+}
+
+// debug: (tag, ns) pairs recorded by the last profiled solve (opt.profile = 1); out must hold 256 entries
+extern "C" int xm_debug_trace(xm_handle* h, unsigned long long* out) {
+    if (!h || !out) return XM_EINVAL;
+    memcpy(out, h->h_stats->trace, sizeof(h->h_stats->trace));
+    return XM_OK;
 }
 
 extern "C" int xm_escape_scale(int n, double* v, const double* s) {

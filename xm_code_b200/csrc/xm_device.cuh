@@ -13,6 +13,7 @@
 //   Q             Qp[i*ldq + k]        — dense, row-major, rows padded to ldq (multiple of 64 doubles, zero filled)
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <stdint.h>
 
 namespace xm {
@@ -23,6 +24,8 @@ constexpr int kPartialBufs = 4;
 constexpr int kPartialStride = 2;   // doubles per CTA slot: [0] = partial sum, [1] = flag from CTA 0
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
+enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, kNumVecR };
+enum ScaId : int { S_S = 0, S_SNEW, S_GS, S_RGS, S_PS, S_RS, S_VS, S_HVS, S_HPS, kNumVecS };
 
 struct LogRec { int k, inner_shown, trstatus, endreason; double loss, gradnorm, delta; };
 
@@ -30,6 +33,8 @@ struct DevStats {
     int exit_code, outer_iters, tcg_iters, qy_products, n_log, aborted;
     double primal, gradnorm, gradtol_out;
     unsigned long long solve_ns, qy_ns, sync_ns;
+    unsigned long long trace[256];   // profile mode: (tag, globaltimer) pairs of CTA 0 / thread 0 around Q.Y product number 200
+    unsigned long long dbg[8];   // CTA 0 / thread 0 breakdown of the Q.Y phases: [0] wait for first tile, [1] later tile waits, [2] tile math, [3] reduce+epilogue
 };
 
 // Everything the device code needs; passed by value as the single kernel parameter.
@@ -42,11 +47,19 @@ struct Dev {
     double lam;
     // launch geometry
     int G, NW, KS, CB, W, cpw, NSW;
-    // state (camera-block layout, 3N*r doubles each)
-    double *Y, *Ynew, *D, *Dnew, *EG, *RG, *P, *Rr, *V, *HV, *HP;
+    // dense Q.Y through a shared-memory ring fed by 2-D tensor-map TMA (use_tma) or by direct streaming loads
+    int use_tma, KC, ST, nbmax, nchunks, stage_doubles;
+    int nprod, NWC;            // TMA path: producer warps (the last nprod warps of the CTA) and consumer warps
+    int box_nb[3];             // cameras per Q box of the three tensor maps (one TMA op moves a whole batch: 3*nb rows x KC)
+    int op_repeat;             // xm_bench_qy: Q.Y phases per launch
+    // state: kNumVecR camera-block vectors (3N*r doubles each, ids VecId) at rbase + id*rstride, kNumVecS scale vectors
+    // (N doubles, index 0 pinned, ids ScaId) at sbase + id*sstride.  When vec_smem != 0 each CTA keeps the slices of
+    // its own cameras in shared memory instead (nobody else ever reads them) and these global arrays are unused.
+    double *rbase; long long rstride;
+    double *sbase; long long sstride;
     double *S6;                // N*6 : sym(Y_i EG_i^T), order 00 01 02 11 12 22
-    // scale state (N doubles each, index 0 pinned)
-    double *s, *snew, *gs, *rgs, *ps, *rs, *vs, *hvs, *hps;
+    int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
+    int profile;               // fine-grained phase timers on (costs a few percent)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)
     double *partials;          // kPartialBufs * G * kPartialStride
     unsigned* bar;             // grid barrier counter (zeroed before each launch)
@@ -84,6 +97,39 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
+
+// ---- mbarrier / TMA primitives (PTX; SASS: SYNCS.*, UTMALDG)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned cnt) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost arrival must end in XM_ESYNC, never in a hung GPU
+__device__ __forceinline__ bool mbar_wait(unsigned long long* b, unsigned parity) {
+#pragma unroll 1
+    for (unsigned it = 0; it < (1u << 22); ++it) if (mbar_try_wait(b, parity)) return true;   // never unroll: code size
+    return false;
+}
+// one 2-D box [rows x cols] global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int col0, int row0, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(col0), "r"(row0), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ double shfl_xor_d(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
 
 // sum over the W lanes of a sub-warp (W power of two, sub-warps aligned): every lane gets the total
@@ -109,25 +155,40 @@ struct Ctx {
     int pbuf;                   // rotating partial buffer
     bool aborted;
     unsigned long long t_qy, t_sync;   // accumulated by CTA 0 thread 0
-    double *Y, *Ynew, *s, *snew, *D, *Dnew;   // swappable state pointers (accepted steps swap instead of copying)
+    unsigned long long dbg0, dbg1, dbg2, dbg3;
+    int trace_n; bool trace_on;
+    __device__ __forceinline__ void tr(int tag) {
+        if (trace_on && trace_n < 127) { d.stats->trace[2 * trace_n] = (unsigned long long)tag; d.stats->trace[2 * trace_n + 1] = gtimer(); ++trace_n; }
+    }
+    // state vectors: base + id*stride (global workspace or this CTA's shared-memory slice, see Dev); accepted steps swap ids
+    double* rbase; long long rstride; double* sbase; long long sstride; double* s6;
+    int iY, iYn, iD, iDn, iS, iSn;
+    __device__ __forceinline__ double* R(int id) const { return rbase + (long long)id * rstride; }
+    __device__ __forceinline__ double* S(int id) const { return sbase + (long long)id * sstride; }
+    // TMA ring state (grid-uniform): running use counter (stage = g % ST, parity = (g / ST) & 1) and how many of the
+    // next phase's uses already have their Q tiles in flight (cross-phase prefetch)
+    double* ring; unsigned long long *fullQ, *fullX, *empty;
+    unsigned g_use; int prefetched;
     double* red;                // smem [NWARPS][3][RP]
     double* bsum;               // smem [NWARPS]
     double* bcast;              // smem [4]
 
-    __device__ Ctx(const Dev& dd, double* red_, double* bsum_, double* bcast_) : d(dd) {
+    __device__ __forceinline__ Ctx(const Dev& dd, double* red_, double* bsum_, double* bcast_) : d(dd) {
         tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
         W = d.W; cpw = d.cpw; sw = lane / W; j = lane % W; NSW = d.NSW;
         slot = warp * cpw + sw;
         act = j < d.r;
         cam_lo = (int)(((long long)blockIdx.x * d.N) / d.G);
         cam_hi = (int)(((long long)(blockIdx.x + 1) * d.N) / d.G);
-        epoch = 0; pbuf = 0; aborted = false; t_qy = 0; t_sync = 0;
+        epoch = 0; pbuf = 0; aborted = false; t_qy = 0; t_sync = 0; dbg0 = dbg1 = dbg2 = dbg3 = 0; trace_n = 0; trace_on = false;
         red = red_; bsum = bsum_; bcast = bcast_;
-        Y = d.Y; Ynew = d.Ynew; s = d.s; snew = d.snew; D = d.D; Dnew = d.Dnew;
+        rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
+        iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
+        ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
     }
 
     // ---- grid-wide barrier (all CTAs co-resident: cooperative launch).  Returns false if it timed out / aborted.
-    __device__ bool grid_sync() {
+    __device__ __forceinline__ bool grid_sync() {
         __syncthreads();
         if (tid == 0) {
             unsigned long long t0 = gtimer();
@@ -137,6 +198,7 @@ struct Ctx {
             atomicAdd(d.bar, 1u);
             int ok = 1;
             unsigned spins = 0;
+#pragma unroll 1
             while (ld_acquire_u32(d.bar) < target) {
                 if ((++spins & 0x3ffu) == 0) {
                     if (*(volatile int*)d.abort_flag) { ok = 0; break; }
@@ -153,7 +215,7 @@ struct Ctx {
     }
 
     // ---- block reduction of one double per thread -> partials[pbuf][cta]; flag travels in slot [1] (CTA 0's counts)
-    __device__ void publish(double v, double flag = 0.0) {
+    __device__ __forceinline__ void publish(double v, double flag = 0.0) {
         v = warpsum(v);
         if (lane == 0) bsum[warp] = v;
         __syncthreads();
@@ -166,7 +228,7 @@ struct Ctx {
         // the following grid_sync() starts with __syncthreads and fences thread 0's stores
     }
     // after grid_sync: every CTA sums the G partials in the same order -> identical bits everywhere
-    __device__ double collect(double* flag_out = nullptr) {
+    __device__ __forceinline__ double collect(double* flag_out = nullptr) {
         if (warp == 0) {
             const double* base = d.partials + (size_t)pbuf * d.G * kPartialStride;
             double t = 0.0;
@@ -304,11 +366,11 @@ __device__ __forceinline__ double epi_hess(Ctx<RP, NT>& c, int i, const double (
     const int r = d.r, W = c.W;
     const bool act = c.act && valid;
     double y[3], p[3], dd[3];
-    ld3(c.Y, i, r, c.j, act, y); ld3(d.P, i, r, c.j, act, p); ld3(c.D, i, r, c.j, act, dd);
-    const double si = c.s[i], psi = d.ps[i], gi = d.gs[i];
+    ld3(c.R(c.iY), i, r, c.j, act, y); ld3(c.R(V_P), i, r, c.j, act, p); ld3(c.R(c.iD), i, r, c.j, act, dd);
+    const double si = c.S(c.iS)[i], psi = c.S(S_PS)[i], gi = c.S(S_GS)[i];
     double S[6];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) S[q] = d.S6[(size_t)i * 6 + q];
+    for (int q = 0; q < 6; ++q) S[q] = c.s6[(size_t)i * 6 + q];
     double e[3], hr[3], t[3], sp[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) { e[a] = 2.0 * E[a]; hr[a] = si * e[a] + psi * dd[a]; }
@@ -324,10 +386,10 @@ __device__ __forceinline__ double epi_hess(Ctx<RP, NT>& c, int i, const double (
     for (int a = 0; a < 3; ++a) rhr[a] = t[a] - my[a];
     hs += 4.0 * d.lam * (3.0 * si * si - 1.0) * psi;
     double rhs = (i == 0) ? 0.0 : (si * si * hs + si * psi * gi);
-    st3(d.HP, i, r, c.j, act, rhr);
+    st3(c.R(V_HP), i, r, c.j, act, rhr);
     double part = act ? (p[0] * rhr[0] + p[1] * rhr[1] + p[2] * rhr[2]) : 0.0;
     if (c.j == 0 && valid) {
-        d.hps[i] = rhs;
+        c.S(S_HPS)[i] = rhs;
         if (i > 0) part += psi * (rhs / (si * si));
     }
     return part;
@@ -349,18 +411,57 @@ __device__ __forceinline__ double epi_obj(Ctx<RP, NT>& c, int i, const double (&
 }
 
 // ------------------------------------------------------------------------------------------------ fused Q.Y phase
-// Streams this CTA's cameras' rows of Q (or BSR block rows) against the operand Xt, reduces inside the CTA and runs
-// the per-camera epilogue straight from shared memory — the Q.Y result never goes to HBM in MODE_HESS / MODE_OBJ.
+// Per-batch tail shared by both dense paths and the BSR path: `red` holds, per warp, the 3*RP sums of its (camera,
+// k-split) task; sub-warp slot q finishes batch camera q: adds the KS partial sums in fixed order and runs the
+// per-camera epilogue straight from shared memory — the Q.Y result never goes to HBM in MODE_HESS / MODE_OBJ.
 template <int RP, int NT, int MODE>
-__device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa) {
+__device__ __forceinline__ double qy_batch_epilogue(Ctx<RP, NT>& c, const ObjArgs& oa, int b0, int nvalid, int KS, int CB) {
+    const Dev& d = c.d;
+    double part = 0.0;
+    if (c.warp * c.cpw < nvalid) {                        // warp-uniform
+        const int q = c.slot;
+        const bool valid = q < nvalid;
+        const int i = valid ? (b0 + q) : b0;              // clamp: idle sub-warps shadow camera b0 without storing
+        double E[3] = {0.0, 0.0, 0.0};
+        if (c.act) {
+            for (int kk = 0; kk < KS; ++kk) {
+                const double* rp = c.red + (size_t)((q < CB ? q : 0) * KS + kk) * 3 * RP;
+                E[0] += rp[0 * RP + c.j]; E[1] += rp[1 * RP + c.j]; E[2] += rp[2 * RP + c.j];
+            }
+        }
+        if (MODE == MODE_OUT) {
+            if (valid && c.act) {
+                double* o = d.op_out_R + (size_t)c.j * d.n3 + 3 * i;   // column-major 3N x r
+                o[0] = d.qy_alpha * E[0]; o[1] = d.qy_alpha * E[1]; o[2] = d.qy_alpha * E[2];
+            }
+        } else if (MODE == MODE_HESS) {
+            part = epi_hess<RP, NT>(c, i, E, valid);
+        } else {
+            part = epi_obj<RP, NT>(c, i, E, oa, valid);
+        }
+    }
+    return part;
+}
+
+template <int RP, int NT>
+__device__ __forceinline__ void warp_reduce_to_red(Ctx<RP, NT>& c, double (&acc)[3][RP]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int jj = 0; jj < RP; ++jj) {
+            const double v = warpsum(acc[a][jj]);          // butterfly: fixed order, every lane gets the total
+            if (c.lane == 0) c.red[(c.warp * 3 + a) * RP + jj] = v;
+        }
+}
+
+// ---- direct-load path (dense without TMA, and block-CSR): all warps of the CTA stream
+template <int RP, int NT, int MODE>
+__device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs& oa) {
     const Dev& d = c.d;
     const int KS = d.KS, CB = d.CB;
     const int cslot = c.warp / KS, ks = c.warp % KS;
     double part = 0.0;
-    unsigned long long t0 = 0;
-    if (blockIdx.x == 0 && c.tid == 0) t0 = gtimer();
-    // column range of this warp's k-split (dense): contiguous runs of 64-column steps
-    const int steps = d.ldq / 64;
+    const int steps = d.ldq / 64;                           // k-split: contiguous runs of 64-column steps
     const int kbeg = (int)(((long long)ks * steps) / KS) * 64;
     const int kend = (int)(((long long)(ks + 1) * steps) / KS) * 64;
     for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
@@ -370,49 +471,188 @@ __device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa) {
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
-        if (cslot < CB && cam < c.cam_hi) {
+        if (cam < c.cam_hi) {
             if (d.Q) qy_sweep_dense<RP>(d, cam, kbeg, kend, c.lane, acc);
             else     qy_sweep_bsr<RP>(d, cam, ks, KS, c.lane, acc);
         }
-        // warp reduction of the 3*RP partial sums (butterfly: fixed order, every lane gets the total)
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int jj = 0; jj < RP; ++jj) {
-                double v = warpsum(acc[a][jj]);
-                if (c.lane == 0) c.red[(c.warp * 3 + a) * RP + jj] = v;
-            }
+        warp_reduce_to_red<RP, NT>(c, acc);
         __syncthreads();
-        // epilogue: sub-warp slot q handles batch camera q
-        const int nvalid = min(CB, c.cam_hi - b0);
-        if (c.warp * c.cpw < nvalid) {                    // warp-uniform
-            const int q = c.slot;
-            const bool valid = q < nvalid;
-            const int i = valid ? (b0 + q) : b0;          // clamp: invalid sub-warps redo camera b0 without storing
-            double E[3] = {0.0, 0.0, 0.0};
-            if (c.act) {
-                for (int kk = 0; kk < KS; ++kk) {
-                    const double* rp = c.red + (size_t)((q < CB ? q : 0) * KS + kk) * 3 * RP;
-                    E[0] += rp[0 * RP + c.j]; E[1] += rp[1 * RP + c.j]; E[2] += rp[2 * RP + c.j];
-                }
-            }
-            if (MODE == MODE_OUT) {
-                if (valid && c.act) {
-                    double* o = d.op_out_R + (size_t)c.j * d.n3 + 3 * i;   // column-major 3N x r
-                    o[0] = d.qy_alpha * E[0]; o[1] = d.qy_alpha * E[1]; o[2] = d.qy_alpha * E[2];
-                }
-            } else {
-                // invalid sub-warps still take part in the shuffles; they run on camera b0 with nothing loaded/stored
-                double pv;
-                if (MODE == MODE_HESS) pv = epi_hess<RP, NT>(c, i, E, valid);
-                else                   pv = epi_obj<RP, NT>(c, i, E, oa, valid);
-                part += pv;
-            }
-        }
+        part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, min(CB, c.cam_hi - b0), KS, CB);
         __syncthreads();
     }
+    return part;
+}
+
+// ---- TMA path: warp NWC is the producer, warps 0..NWC-1 consume [3 rows x KC] boxes of their camera from a ring of ST
+// stages in shared memory (one cp.async.bulk.tensor.2d per camera per chunk + one for the operand chunk).  The ring
+// never drains between Q.Y phases: when a phase ends the producer immediately re-arms the first min(ST, uses) stages
+// with the NEXT phase's Q tiles (Q does not depend on the operand), so HBM keeps streaming while the CTA runs the
+// per-camera phases and waits in grid barriers; only the small operand boxes are issued after the barrier.
+template <int RP, int NT, int MODE>
+__device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa, const CUtensorMap* mapQ3, const CUtensorMap* mapX,
+                                               bool prefetch_next) {
+    const Dev& d = c.d;
+    const int NWC = d.NWC, nprod = d.nprod;
+    const int KS = d.KS, CB = d.CB, KC = d.KC, ST = d.ST, nchunks = d.nchunks;
+    const int ncam = c.cam_hi - c.cam_lo;
+    const int nbatches = (ncam + CB - 1) / CB;
+    const int uses = nbatches * nchunks;
+    const unsigned g0 = c.g_use;
+    const int pre = c.prefetched;
+    const int npre = prefetch_next ? min(ST, uses) : 0;
+    const size_t stage_doubles = (size_t)d.stage_doubles;
+    const size_t xoff = (size_t)3 * d.nbmax * KC;           // operand rows sit after the Q rows of a stage
+    double part = 0.0;
+    if (c.warp >= NWC) {
+        // ------------------------------------------------ producers: warp NWC+p owns the stages s = p (mod nprod).  Measured on B200:
+        // one producer warp is enough (1..4 give the same chunk rate), so nprod = 1 by default
+        const int pw = c.warp - NWC;
+        // the operand was written through the generic proxy (other CTAs, before the grid barrier): order it before the
+        // async-proxy (TMA) reads issued below
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        bool ok = true;
+        for (int u = 0; u < uses + npre && ok; ++u) {
+            const bool spec = u >= uses;                    // speculative: Q tiles of the next phase
+            const unsigned g = g0 + u;
+            const int s = g % ST; const unsigned par = (g / ST) & 1;
+            if (s % nprod != pw) continue;                  // stage affinity: all uses of a stage are issued, in order, by one warp
+                                                            // (parity waits cannot tell phase k from k+2, so a stage must never have two issuers)
+            const int uu = spec ? u - uses : u;
+            const int bi = uu / nchunks, ch = uu - bi * nchunks;
+            const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
+            double* st = c.ring + (size_t)s * stage_doubles;
+            if (spec || u >= pre) {                         // Q tiles not in flight yet
+                if (g >= (unsigned)ST) {                    // stage must have been released by every consumer warp
+                    int w = 1;
+                    if (c.lane == 0) w = mbar_wait(&c.empty[s], par ^ 1) ? 1 : 0;
+                    w = __shfl_sync(0xffffffffu, w, 0);
+                    if (!w) { ok = false; break; }
+                }
+                if (c.lane == 0) {      // ONE op for the whole batch: [3*nb rows x KC] (TMA cost is per op, ~60-100 ns)
+                    const CUtensorMap* mq = (nb == d.box_nb[0]) ? mapQ3 : (nb == d.box_nb[1]) ? mapQ3 + 1 : mapQ3 + 2;
+                    mbar_expect_tx(&c.fullQ[s], (unsigned)(3 * nb * KC * sizeof(double)));
+                    tma_load_2d(st, mq, ch * KC, 3 * b0, &c.fullQ[s]);
+                }
+            }
+            if (!spec && c.lane == 0) {
+                mbar_expect_tx(&c.fullX[s], (unsigned)(d.r * KC * sizeof(double)));
+                tma_load_2d(st + xoff, mapX, ch * KC, 0, &c.fullX[s]);
+            }
+        }
+        if (!ok && c.lane == 0) *(volatile int*)d.abort_flag = 1;
+    } else {
+        // ------------------------------------------------ consumers
+        const int cslot = c.warp / KS, ks = c.warp % KS;
+        bool ok = true;
+        for (int bi = 0; bi < nbatches && ok; ++bi) {
+            const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
+            const bool has = cslot < nb;
+            double acc[3][RP];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const unsigned g = g0 + bi * nchunks + ch;
+                const int s = g % ST; const unsigned par = (g / ST) & 1;
+                const bool tm = (d.profile && blockIdx.x == 0 && c.tid == 0);
+                unsigned long long tw0 = 0; if (tm) tw0 = gtimer();
+                if (!mbar_wait(&c.fullQ[s], par) || !mbar_wait(&c.fullX[s], par)) { ok = false; break; }
+                c.tr(100 + ch);
+                unsigned long long tw1 = 0; if (tm) { tw1 = gtimer(); if (bi == 0 && ch == 0) c.dbg0 += tw1 - tw0; else c.dbg1 += tw1 - tw0; }
+                if (has && (ch % KS) == ks) {
+                    const double* st = c.ring + (size_t)s * stage_doubles;
+                    const double* q0 = st + (size_t)(3 * cslot) * KC;
+                    const double* xs = st + xoff;
+                    for (int k = 2 * c.lane; k < KC; k += 64) {
+                        const double2 a0 = *reinterpret_cast<const double2*>(q0 + k);
+                        const double2 a1 = *reinterpret_cast<const double2*>(q0 + KC + k);
+                        const double2 a2 = *reinterpret_cast<const double2*>(q0 + 2 * KC + k);
+#pragma unroll
+                        for (int jj = 0; jj < RP; ++jj) {
+                            if (jj < d.r) {
+                                const double2 x = *reinterpret_cast<const double2*>(xs + (size_t)jj * KC + k);
+                                acc[0][jj] = fma(a0.x, x.x, acc[0][jj]); acc[0][jj] = fma(a0.y, x.y, acc[0][jj]);
+                                acc[1][jj] = fma(a1.x, x.x, acc[1][jj]); acc[1][jj] = fma(a1.y, x.y, acc[1][jj]);
+                                acc[2][jj] = fma(a2.x, x.x, acc[2][jj]); acc[2][jj] = fma(a2.y, x.y, acc[2][jj]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (c.lane == 0) mbar_arrive(&c.empty[s]);
+                if (tm) c.dbg2 += gtimer() - tw1;
+            }
+            c.tr(200);
+            unsigned long long te0 = 0; if (d.profile && blockIdx.x == 0 && c.tid == 0) te0 = gtimer();
+            warp_reduce_to_red<RP, NT>(c, acc);
+            named_bar_sync(1, NWC * 32);                    // consumers only: the producer is busy re-arming the ring
+            part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, nb, KS, CB);
+            named_bar_sync(1, NWC * 32);
+            if (d.profile && blockIdx.x == 0 && c.tid == 0) c.dbg3 += gtimer() - te0;
+        }
+        if (!ok && c.lane == 0) *(volatile int*)d.abort_flag = 1;
+    }
+    c.g_use = g0 + (unsigned)uses;
+    c.prefetched = npre;
+    return part;
+}
+
+// PATH: 0 = dense through the TMA ring, 1 = direct loads (dense qy_variant=1, and block-CSR).  A kernel is compiled for one
+// path only, so the register budget of the persistent kernel is not set by the path it does not run.
+template <int RP, int NT, int MODE, int PATH>
+__device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa, const CUtensorMap* mapQ, const CUtensorMap* mapX,
+                                           bool prefetch_next = true) {     // mapQ: array of 3 maps (box heights d.box_nb[])
+    unsigned long long t0 = 0;
+    if (blockIdx.x == 0 && c.tid == 0) t0 = gtimer();
+    double part;
+    if (PATH == 0) part = qy_phase_tma<RP, NT, MODE>(c, oa, mapQ, mapX, prefetch_next);
+    else           part = qy_phase_direct<RP, NT, MODE>(c, oa);
     if (blockIdx.x == 0 && c.tid == 0) c.t_qy += gtimer() - t0;
     return part;
+}
+
+// shared-memory set-up (once per kernel): [per-CTA state vectors, if they fit][TMA ring + its mbarriers]
+template <int RP, int NT>
+__device__ __forceinline__ void ring_init(Ctx<RP, NT>& c, unsigned char* dyn_smem) {
+    const Dev& d = c.d;
+    const int NWC = d.NWC;
+    unsigned char* base = (unsigned char*)(((uintptr_t)dyn_smem + 127) & ~(uintptr_t)127);
+    if (d.vec_smem) {
+        // slices of this CTA's own cameras; the "- cam_lo" bias lets every phase keep indexing by global camera id
+        const long long cpc = d.cpc_max, r3 = 3LL * d.r;
+        double* vr = reinterpret_cast<double*>(base);
+        double* vs = vr + (long long)kNumVecR * cpc * r3;
+        double* v6 = vs + (long long)kNumVecS * cpc;
+        c.rstride = cpc * r3; c.rbase = vr - (long long)c.cam_lo * r3;
+        c.sstride = cpc;      c.sbase = vs - (long long)c.cam_lo;
+        c.s6 = v6 - (long long)c.cam_lo * 6;
+        const size_t bytes = (size_t)((kNumVecR * cpc * r3 + kNumVecS * cpc + 6 * cpc) * sizeof(double));
+        base += (bytes + 127) & ~(size_t)127;
+    }
+    if (!d.use_tma) { __syncthreads(); return; }
+    c.ring = reinterpret_cast<double*>(base);
+    c.fullQ = reinterpret_cast<unsigned long long*>(c.ring + (size_t)d.ST * d.stage_doubles);
+    c.fullX = c.fullQ + d.ST;
+    c.empty = c.fullX + d.ST;
+    if (c.tid == 0) {
+        for (int s = 0; s < d.ST; ++s) { mbar_init(&c.fullQ[s], 1); mbar_init(&c.fullX[s], 1); mbar_init(&c.empty[s], NWC); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+template <int RP, int NT>
+__device__ __forceinline__ void ring_drain(Ctx<RP, NT>& c) {
+    const Dev& d = c.d;
+    if (!d.use_tma) return;
+    __syncthreads();
+    if (c.tid == 0) {
+        for (int u = 0; u < c.prefetched; ++u) {
+            const unsigned g = c.g_use + u;
+            (void)mbar_wait(&c.fullQ[g % d.ST], (g / d.ST) & 1);
+        }
+    }
+    __syncthreads();
 }
 
 }  // namespace xm

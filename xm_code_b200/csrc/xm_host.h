@@ -27,6 +27,10 @@ struct xm_handle {
     // pinned host mirrors
     xm::DevStats* h_stats = nullptr; xm::LogRec* h_log = nullptr;
     int launches = 0;
+    // TMA descriptors (2-D tensor maps) for the dense Q and the current operand buffer
+    CUtensorMap mapQ[3]{}, mapX{};
+    void* encode_tiled = nullptr;       // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
+    int smem_optin = 0;                 // max opt-in dynamic shared memory per block
 };
 
 #define XM_CUDA(h, call)                                                                           \

@@ -1,0 +1,54 @@
+// xm_inst.cu — instantiations of the persistent solve kernel and the op-level kernel for one group of padded ranks.
+// Compiled three times (-DXM_INST_GROUP=0/1/2) so the build runs in parallel; see xm_capi.cu:launch_any.
+#include "xm_host.h"
+#include "xm_solve.cuh"
+
+using namespace xm;
+
+#ifndef XM_INST_GROUP
+#error "compile with -DXM_INST_GROUP=0|1|2"
+#endif
+
+template <int RP, int NT>
+static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+    const void* fn;
+    if (kind == 0) fn = d.use_tma ? (const void*)xm_solve_kernel<RP, NT, 0> : (const void*)xm_solve_kernel<RP, NT, 1>;
+    else           fn = d.use_tma ? (const void*)xm_ops_kernel<RP, NT, 0> : (const void*)xm_ops_kernel<RP, NT, 1>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    if (kind == 0) {
+        void* args[] = {(void*)&d, (void*)h->mapQ, (void*)&h->mapX};
+        return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(NT), args, dyn, st);
+    }
+    void* args[] = {(void*)&d, (void*)h->mapQ, (void*)&h->mapX, (void*)&opcode};
+    return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(NT), args, dyn, st);
+}
+
+#if XM_INST_GROUP == 0
+cudaError_t xm_launch_group0(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+    switch (RP) {
+        case 3: return launch_t<3, 512>(kind, h, d, opcode, dyn, st);
+        case 4: return launch_t<4, 512>(kind, h, d, opcode, dyn, st);
+        case 5: return launch_t<5, 512>(kind, h, d, opcode, dyn, st);
+    }
+    return cudaErrorInvalidValue;
+}
+#elif XM_INST_GROUP == 1
+cudaError_t xm_launch_group1(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+    switch (RP) {
+        case 6: return launch_t<6, 512>(kind, h, d, opcode, dyn, st);
+        case 8: return launch_t<8, 512>(kind, h, d, opcode, dyn, st);
+        case 10: return launch_t<10, 512>(kind, h, d, opcode, dyn, st);
+    }
+    return cudaErrorInvalidValue;
+}
+#else
+cudaError_t xm_launch_group2(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+    switch (RP) {
+        case 12: return launch_t<12, 256>(kind, h, d, opcode, dyn, st);
+        case 16: return launch_t<16, 256>(kind, h, d, opcode, dyn, st);
+        case 20: return launch_t<20, 256>(kind, h, d, opcode, dyn, st);
+    }
+    return cudaErrorInvalidValue;
+}
+#endif

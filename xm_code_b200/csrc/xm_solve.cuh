@@ -5,6 +5,8 @@
 
 namespace xm {
 
+struct QMaps { CUtensorMap m[3]; };   // Q tensor maps for the (at most three) distinct batch heights of a launch
+
 // All per-camera phases iterate the CTA's own cameras with the same sub-warp -> camera mapping.
 // The loop trip count is warp-uniform; sub-warps past the end run with valid=false on a clamped (in-range) camera
 // so that they can take part in the sub-warp shuffles without loading or storing anything.
@@ -23,9 +25,9 @@ __device__ __forceinline__ void phase_load_point(Ctx<RP, NT>& c, const double* R
             double y[3];
             const double* p = R0 + (size_t)c.j * d.n3 + 3 * i;
             y[0] = p[0]; y[1] = p[1]; y[2] = p[2];
-            st3(c.Y, i, d.r, c.j, true, y);
+            st3(c.R(c.iY), i, d.r, c.j, true, y);
         }
-        if (valid && c.j == 0) c.s[i] = (i == 0) ? 1.0 : s0[i];
+        if (valid && c.j == 0) c.S(c.iS)[i] = (i == 0) ? 1.0 : s0[i];
     }
 }
 // ---- exit: camera-block state -> wire layout
@@ -68,15 +70,15 @@ __device__ __forceinline__ void phase_ls_trial(Ctx<RP, NT>& c, double alpha) {
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double a[3];
-        ld3(c.Y, i, d.r, c.j, act, a);
+        ld3(c.R(c.iY), i, d.r, c.j, act, a);
         if (act && c.j == d.r - 1) {
             a[0] -= alpha * d.vdir[3 * i]; a[1] -= alpha * d.vdir[3 * i + 1]; a[2] -= alpha * d.vdir[3 * i + 2];
         }
         if (!act && valid) { a[0] = a[1] = a[2] = 0.0; }
         if (!valid) { a[0] = (c.j == 0); a[1] = (c.j == 1); a[2] = (c.j == 2); }   // keep idle sub-warps finite
         mgs3(a, c.W);
-        st3(c.Ynew, i, d.r, c.j, act, a);
-        const double si = valid ? c.s[i] : 0.0;
+        st3(c.R(c.iYn), i, d.r, c.j, act, a);
+        const double si = valid ? c.S(c.iS)[i] : 0.0;
         double x[3] = {si * a[0], si * a[1], si * a[2]};
         st_operand(d.Xt, d.ldq, i, c.j, act, x);
     }
@@ -93,8 +95,8 @@ __device__ __forceinline__ double phase_grad(Ctx<RP, NT>& c, bool build_operand)
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double y[3], dd[3];
-        ld3(c.Y, i, r, c.j, act, y); ld3(c.D, i, r, c.j, act, dd);
-        const double si = valid ? c.s[i] : 1.0;
+        ld3(c.R(c.iY), i, r, c.j, act, y); ld3(c.R(c.iD), i, r, c.j, act, dd);
+        const double si = valid ? c.S(c.iS)[i] : 1.0;
         double G[3] = {si * dd[0], si * dd[1], si * dd[2]};
         double g = subsum(dd[0] * y[0] + dd[1] * y[1] + dd[2] * y[2], W);
         g += 4.0 * d.lam * (si * si - 1.0) * si;
@@ -106,12 +108,12 @@ __device__ __forceinline__ double phase_grad(Ctx<RP, NT>& c, bool build_operand)
 #pragma unroll
         for (int a = 0; a < 3; ++a) { rg[a] = G[a] - sy[a]; p[a] = -rg[a]; }
         const double rgs = (i == 0) ? 0.0 : si * si * g;
-        st3(d.EG, i, r, c.j, act, G); st3(d.RG, i, r, c.j, act, rg); st3(d.Rr, i, r, c.j, act, rg);
-        st3(d.P, i, r, c.j, act, p); st3(d.V, i, r, c.j, act, z); st3(d.HV, i, r, c.j, act, z);
+        st3(c.R(V_EG), i, r, c.j, act, G); st3(c.R(V_RG), i, r, c.j, act, rg); st3(c.R(V_RR), i, r, c.j, act, rg);
+        st3(c.R(V_P), i, r, c.j, act, p); st3(c.R(V_V), i, r, c.j, act, z); st3(c.R(V_HV), i, r, c.j, act, z);
         if (valid && c.j == 0) {
-            d.gs[i] = g; d.rgs[i] = rgs; d.rs[i] = rgs; d.ps[i] = -rgs; d.vs[i] = 0.0; d.hvs[i] = 0.0;
+            c.S(S_GS)[i] = g; c.S(S_RGS)[i] = rgs; c.S(S_RS)[i] = rgs; c.S(S_PS)[i] = -rgs; c.S(S_VS)[i] = 0.0; c.S(S_HVS)[i] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) d.S6[(size_t)i * 6 + q] = S[q];
+            for (int q = 0; q < 6; ++q) c.s6[(size_t)i * 6 + q] = S[q];
             if (i > 0) { const double t = rgs / si; part += t * t; }
         }
         if (act) part += rg[0] * rg[0] + rg[1] * rg[1] + rg[2] * rg[2];
@@ -134,19 +136,19 @@ __device__ __forceinline__ double phase_update(Ctx<RP, NT>& c, double alpha) {
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double p[3], hp[3], v[3], rr[3], hv[3];
-        ld3(d.P, i, r, c.j, act, p); ld3(d.HP, i, r, c.j, act, hp); ld3(d.V, i, r, c.j, act, v);
-        ld3(d.Rr, i, r, c.j, act, rr); ld3(d.HV, i, r, c.j, act, hv);
+        ld3(c.R(V_P), i, r, c.j, act, p); ld3(c.R(V_HP), i, r, c.j, act, hp); ld3(c.R(V_V), i, r, c.j, act, v);
+        ld3(c.R(V_RR), i, r, c.j, act, rr); ld3(c.R(V_HV), i, r, c.j, act, hv);
 #pragma unroll
         for (int a = 0; a < 3; ++a) { v[a] += alpha * p[a]; rr[a] += alpha * hp[a]; hv[a] += alpha * hp[a]; }
-        st3(d.V, i, r, c.j, act, v); st3(d.Rr, i, r, c.j, act, rr); st3(d.HV, i, r, c.j, act, hv);
+        st3(c.R(V_V), i, r, c.j, act, v); st3(c.R(V_RR), i, r, c.j, act, rr); st3(c.R(V_HV), i, r, c.j, act, hv);
         if (act) part += rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2];
         if (valid && c.j == 0 && i > 0) {
-            const double psi = d.ps[i], hpsi = d.hps[i];
-            d.vs[i] += alpha * psi;
-            const double rsi = d.rs[i] + alpha * hpsi;
-            d.rs[i] = rsi;
-            d.hvs[i] += alpha * hpsi;
-            const double t = rsi / c.s[i];
+            const double psi = c.S(S_PS)[i], hpsi = c.S(S_HPS)[i];
+            c.S(S_VS)[i] += alpha * psi;
+            const double rsi = c.S(S_RS)[i] + alpha * hpsi;
+            c.S(S_RS)[i] = rsi;
+            c.S(S_HVS)[i] += alpha * hpsi;
+            const double t = rsi / c.S(c.iS)[i];
             part += t * t;
         }
     }
@@ -162,11 +164,11 @@ __device__ __forceinline__ void phase_tau(Ctx<RP, NT>& c, double tau) {
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double p[3], hp[3], v[3], hv[3];
-        ld3(d.P, i, r, c.j, act, p); ld3(d.HP, i, r, c.j, act, hp); ld3(d.V, i, r, c.j, act, v); ld3(d.HV, i, r, c.j, act, hv);
+        ld3(c.R(V_P), i, r, c.j, act, p); ld3(c.R(V_HP), i, r, c.j, act, hp); ld3(c.R(V_V), i, r, c.j, act, v); ld3(c.R(V_HV), i, r, c.j, act, hv);
 #pragma unroll
         for (int a = 0; a < 3; ++a) { v[a] += tau * p[a]; hv[a] += tau * hp[a]; }
-        st3(d.V, i, r, c.j, act, v); st3(d.HV, i, r, c.j, act, hv);
-        if (valid && c.j == 0 && i > 0) { d.vs[i] += tau * d.ps[i]; d.hvs[i] += tau * d.hps[i]; }
+        st3(c.R(V_V), i, r, c.j, act, v); st3(c.R(V_HV), i, r, c.j, act, hv);
+        if (valid && c.j == 0 && i > 0) { c.S(S_VS)[i] += tau * c.S(S_PS)[i]; c.S(S_HVS)[i] += tau * c.S(S_HPS)[i]; }
     }
 }
 
@@ -179,14 +181,14 @@ __device__ __forceinline__ void phase_dir(Ctx<RP, NT>& c, double beta) {
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double p[3], rr[3], y[3];
-        ld3(d.P, i, r, c.j, act, p); ld3(d.Rr, i, r, c.j, act, rr); ld3(c.Y, i, r, c.j, act, y);
-        const double si = valid ? c.s[i] : 0.0;
+        ld3(c.R(V_P), i, r, c.j, act, p); ld3(c.R(V_RR), i, r, c.j, act, rr); ld3(c.R(c.iY), i, r, c.j, act, y);
+        const double si = valid ? c.S(c.iS)[i] : 0.0;
         double psi = 0.0;
-        if (valid && i > 0) psi = beta * d.ps[i] - d.rs[i];
+        if (valid && i > 0) psi = beta * c.S(S_PS)[i] - c.S(S_RS)[i];
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[a] = beta * p[a] - rr[a];
-        st3(d.P, i, r, c.j, act, p);
-        if (valid && c.j == 0 && i > 0) d.ps[i] = psi;
+        st3(c.R(V_P), i, r, c.j, act, p);
+        if (valid && c.j == 0 && i > 0) c.S(S_PS)[i] = psi;
         double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
         st_operand(d.Xt, d.ldq, i, c.j, act, x);
     }
@@ -204,25 +206,25 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double y[3], v[3];
-        ld3(c.Y, i, r, c.j, act, y); ld3(etaR, i, r, c.j, act, v);
-        const double si = valid ? c.s[i] : 1.0;
+        ld3(c.R(c.iY), i, r, c.j, act, y); ld3(etaR, i, r, c.j, act, v);
+        const double si = valid ? c.S(c.iS)[i] : 1.0;
         const double vsi = (valid && i > 0) ? etas[i] : 0.0;
         if (with_model) {
             double hv[3], rg[3];
-            ld3(d.HV, i, r, c.j, act, hv); ld3(d.RG, i, r, c.j, act, rg);
+            ld3(c.R(V_HV), i, r, c.j, act, hv); ld3(c.R(V_RG), i, r, c.j, act, rg);
             if (act) part += 0.5 * (v[0] * hv[0] + v[1] * hv[1] + v[2] * hv[2]) + (v[0] * rg[0] + v[1] * rg[1] + v[2] * rg[2]);
             if (valid && c.j == 0 && i > 0) {
                 const double vsds = vsi / (si * si);
-                part += 0.5 * vsds * d.hvs[i] + vsds * d.rgs[i];
+                part += 0.5 * vsds * c.S(S_HVS)[i] + vsds * c.S(S_RGS)[i];
             }
         }
         double a[3] = {y[0] + lr * v[0], y[1] + lr * v[1], y[2] + lr * v[2]};
         if (!act) { a[0] = a[1] = a[2] = 0.0; }
         if (!valid) { a[0] = (c.j == 0); a[1] = (c.j == 1); a[2] = (c.j == 2); }
         mgs3(a, c.W);
-        st3(c.Ynew, i, r, c.j, act, a);
+        st3(c.R(c.iYn), i, r, c.j, act, a);
         const double sn = (i == 0) ? si : si * exp(lr * vsi / si);   // positiveManifoldRetractionKernal :18-24
-        if (valid && c.j == 0) c.snew[i] = sn;
+        if (valid && c.j == 0) c.S(c.iSn)[i] = sn;
         double x[3] = {sn * a[0], sn * a[1], sn * a[2]};
         st_operand(d.Xt, d.ldq, i, c.j, act, x);
     }
@@ -232,12 +234,15 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
 #define XM_GSYNC(c) do { if (!(c).grid_sync()) goto xm_abort; } while (0)
 
 // ================================================================================================ the solver
-template <int RP, int NT>
-__global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
+template <int RP, int NT, int PATH>
+__global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
+                                                         const __grid_constant__ CUtensorMap mapX) {
     __shared__ double red[(NT / 32) * 3 * RP];
     __shared__ double bsum[NT / 32];
     __shared__ double bcast[4];
+    extern __shared__ unsigned char dyn_smem[];
     Ctx<RP, NT> c(d, red, bsum, bcast);
+    ring_init(c, dyn_smem);
     const bool lead = (blockIdx.x == 0 && c.tid == 0);
     const unsigned long long t_kernel0 = gtimer();
     unsigned long long t_loop0 = t_kernel0;
@@ -254,11 +259,11 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
     double loss_k = 0.0, gradnorm = 0.0, f0 = 0.0, fnew = 0.0;
 
     phase_load_point(c, d.R0, d.s0);
-    phase_operand_sR(c, c.Y, c.s);
+    phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
     XM_GSYNC(c);
     {   // f0 = objc(sR,s) and D = 2 Q sR at the start point (:362 / :422)
-        ObjArgs oa{c.Y, c.s, c.D};
-        double part = qy_phase<RP, NT, MODE_OBJ>(c, oa);
+        ObjArgs oa{c.R(c.iY), c.S(c.iS), c.R(c.iD)};
+        double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX);
         c.publish(part); XM_GSYNC(c); f0 = c.collect(); nqy++;
     }
     loss_k = f0;
@@ -269,17 +274,17 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
             if (!first) alpha = alpha / 2;                                   // :378
             phase_ls_trial(c, alpha);
             XM_GSYNC(c);
-            ObjArgs oa{c.Ynew, c.s, c.Dnew};
-            double part = qy_phase<RP, NT, MODE_OBJ>(c, oa);
+            ObjArgs oa{c.R(c.iYn), c.S(c.iS), c.R(c.iDn)};
+            double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX);
             c.publish(part); XM_GSYNC(c); fnew = c.collect(); nqy++;
             if (!first && alpha < 1e-20) { failed = true; break; }            // :384-391 (tested after the evaluation)
             if (!(fnew > f0)) break;                                         // while (f > f0)
             first = false;
         }
         if (!failed && (f0 - fnew > 0)) {                                    // :394
-            double* t = c.Y; c.Y = c.Ynew; c.Ynew = t;                      // R_T, R <- new (:396-397)
+            int t = c.iY; c.iY = c.iYn; c.iYn = t;                      // R_T, R <- new (:396-397)
             if (d.replicate_stale_sr) { d_stale = true; }                    // quirk Q3: sR, loss[0], D stay at the old point
-            else { t = c.D; c.D = c.Dnew; c.Dnew = t; loss_k = fnew; }
+            else { t = c.iD; c.iD = c.iDn; c.iDn = t; loss_k = fnew; }
         } else {
             exit_code = -1;                                                   // line search failed: primal = -1 (:384-405)
             loss_k = -1.0;
@@ -310,8 +315,12 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
 
         for (i_inner = 0; i_inner < d.max_inner; ++i_inner) {                       // :559-664
             ObjArgs oa{nullptr, nullptr, nullptr};
-            const double ph = qy_phase<RP, NT, MODE_HESS>(c, oa);
+            c.trace_on = (d.profile && lead && nqy >= 200 && nqy < 202);
+            c.tr(1);
+            const double ph = qy_phase<RP, NT, MODE_HESS, PATH>(c, oa, mapsQ.m, &mapX);
+            c.tr(2);
             c.publish(ph); XM_GSYNC(c);
+            c.tr(3);
             const double pHp = c.collect(); nqy++;
             const double alpha = rdotr / pHp;                                       // :566
             if (rdotr < 1e-15) { endreason = 5; break; }                            // :572-576
@@ -323,13 +332,19 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
                 endreason = (alpha <= 0) ? 1 : 2;
                 break;
             }
+            c.tr(4);
             const double pr = phase_update(c, alpha);
+            c.tr(5);
             c.publish(pr); XM_GSYNC(c);
+            c.tr(6);
             const double rdotr_new = c.collect();                                   // :626
             if (sqrt(rdotr_new) < gradnorm * fmin(gradnorm, 0.1)) { endreason = 3; break; }   // :627-630
             const double beta = rdotr_new / rdotr;
+            c.tr(7);
             phase_dir(c, beta);
+            c.tr(8);
             XM_GSYNC(c);
+            c.tr(9);
             const double nvv = vdotv + 2 * alpha * vdotp + alpha * alpha * pdotp;   // :642-644
             const double nvp = beta * (vdotp + alpha * pdotp);
             const double npp = beta * beta * pdotp + rdotr_new;
@@ -338,13 +353,13 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
         }
         totalite += i_inner + 1;                                                    // :666
 
-        const double pm = phase_model_retract(c, d.V, d.vs, 1.0, true);
+        const double pm = phase_model_retract(c, c.R(V_V), c.S(S_VS), 1.0, true);
         c.publish(pm); XM_GSYNC(c);
         const double loss_qu = c.collect();
         if (loss_qu >= 0) { exit_code = 4; break; }                                 // :669-672
         {
-            ObjArgs oa{c.Ynew, c.snew, c.Dnew};
-            const double pf = qy_phase<RP, NT, MODE_OBJ>(c, oa);
+            ObjArgs oa{c.R(c.iYn), c.S(c.iSn), c.R(c.iDn)};
+            const double pf = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX);
             c.publish(pf); XM_GSYNC(c); fnew = c.collect(); nqy++;                 // loss[k+1] (:678)
         }
         const double rou = (fnew - loss_k) / loss_qu;                               // :680
@@ -355,22 +370,22 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
             delta = delta * 1e-3; shrink_count = 0;
             if (delta < 1e-20) {                                                    // :697-700
                 // the reference breaks here with R,s already overwritten by the new point and primal = loss[k]
-                double* t = c.Y; c.Y = c.Ynew; c.Ynew = t; t = c.s; c.s = c.snew; c.snew = t;
+                int t = c.iY; c.iY = c.iYn; c.iYn = t; t = c.iS; c.iS = c.iSn; c.iSn = t;
                 exit_code = 5; break;
             }
         }
         if ((fnew > loss_k) || (rou < 0.1)) {                                       // :702 reject (bestloss == loss[k])
             trstatus = 3;                                                           // loss[k+1] = bestloss
             if (d_stale) {          // the reference recomputes everything from the restored (fresh) sR next iteration
-                phase_operand_sR(c, c.Y, c.s);
+                phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
                 XM_GSYNC(c);
-                ObjArgs oa{c.Y, c.s, c.D};
-                (void)qy_phase<RP, NT, MODE_OBJ>(c, oa); nqy++;
+                ObjArgs oa{c.R(c.iY), c.S(c.iS), c.R(c.iD)};
+                (void)qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX); nqy++;
                 XM_GSYNC(c);        // nobody may rewrite the operand while another CTA is still sweeping it
             }
         } else {
-            double* t = c.Y; c.Y = c.Ynew; c.Ynew = t; t = c.s; c.s = c.snew; c.snew = t;
-            t = c.D; c.D = c.Dnew; c.Dnew = t;
+            int t = c.iY; c.iY = c.iYn; c.iYn = t; t = c.iS; c.iS = c.iSn; c.iSn = t;
+            t = c.iD; c.iD = c.iDn; c.iDn = t;
             loss_k = fnew;
         }
         d_stale = false;
@@ -378,16 +393,19 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const Dev d) {
     if (k >= d.max_outer && exit_code == 0) exit_code = 6;
 
 xm_finish:
-    phase_store_point(c, c.Y, c.s, d.R_out, d.s_out);
+    ring_drain(c);
+    phase_store_point(c, c.R(c.iY), c.S(c.iS), d.R_out, d.s_out);
     if (lead) {
         DevStats& S = *d.stats;
         S.exit_code = exit_code; S.outer_iters = k; S.tcg_iters = totalite; S.qy_products = nqy;
         S.n_log = n_log < kLogCap ? n_log : kLogCap; S.aborted = 0;
         S.primal = loss_k; S.gradnorm = gradnorm; S.gradtol_out = gradtol;
         S.solve_ns = gtimer() - t_kernel0; S.qy_ns = c.t_qy; S.sync_ns = c.t_sync;
+        S.dbg[0] = c.dbg0; S.dbg[1] = c.dbg1; S.dbg[2] = c.dbg2; S.dbg[3] = c.dbg3;
     }
     return;
 xm_abort:
+    ring_drain(c);
     if (lead) { d.stats->aborted = 1; d.stats->exit_code = 0; }
     return;
 }
@@ -398,15 +416,30 @@ xm_abort:
 //         2 = Riemannian gradient at (R0,s0)                        -> op_out_R = rgradR, op_out_s = rgrads, scalar[0] = gradnorm
 //         3 = Riemannian Hessian-vector at (R0,s0) along (P,ps)     -> op_out_R = HpR, op_out_s = Hps
 //         4 = retraction of (R0,s0) along (P,ps) with step op_lr    -> op_out_R = Rn, op_out_s = sn
-template <int RP, int NT>
-__global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const Dev d, const int opcode) {
+template <int RP, int NT, int PATH>
+__global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
+                                                       const __grid_constant__ CUtensorMap mapX, const int opcode) {
     __shared__ double red[(NT / 32) * 3 * RP];
     __shared__ double bsum[NT / 32];
     __shared__ double bcast[4];
+    extern __shared__ unsigned char dyn_smem[];
     Ctx<RP, NT> c(d, red, bsum, bcast);
+    ring_init(c, dyn_smem);
     if (opcode == 0) {
         ObjArgs oa{nullptr, nullptr, nullptr};
-        (void)qy_phase<RP, NT, MODE_OUT>(c, oa);
+        // op_repeat > 1 (xm_bench_qy): back-to-back products inside one launch, ring prefetch across them as in the solver
+        const int nrep = d.op_repeat < 0 ? -d.op_repeat : d.op_repeat;
+        for (int rep = 0; rep < nrep; ++rep) {
+            (void)qy_phase<RP, NT, MODE_OUT, PATH>(c, oa, mapsQ.m, &mapX, rep + 1 < nrep);
+            if (d.op_repeat < 0) { XM_GSYNC(c); }      // lock-step products, as inside the solver
+            else __syncthreads();
+        }
+        if (blockIdx.x == 0 && c.tid == 0) { d.stats->dbg[0] = c.dbg0; d.stats->dbg[1] = c.dbg1; d.stats->dbg[2] = c.dbg2; d.stats->dbg[3] = c.dbg3; d.stats->qy_ns = c.t_qy; d.stats->sync_ns = c.t_sync; }
+        return;
+    }
+    if (opcode == 5) {                 // grid-barrier micro-benchmark: |op_repeat| barriers back to back
+        const int nrep = d.op_repeat < 0 ? -d.op_repeat : d.op_repeat;
+        for (int rep = 0; rep < nrep; ++rep) { XM_GSYNC(c); }
         return;
     }
     phase_load_point(c, d.R0, d.s0);
@@ -417,19 +450,19 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const Dev d, const int op
             if (act) {
                 const double* p = d.op_in_P + (size_t)c.j * d.n3 + 3 * i;
                 double v[3] = {p[0], p[1], p[2]};
-                st3(d.V, i, d.r, c.j, true, v);
+                st3(c.R(V_V), i, d.r, c.j, true, v);
             }
-            if (valid && c.j == 0) d.vs[i] = (i == 0) ? 0.0 : d.op_in_ps[i];
+            if (valid && c.j == 0) c.S(S_VS)[i] = (i == 0) ? 0.0 : d.op_in_ps[i];
         }
-        (void)phase_model_retract(c, d.V, d.vs, d.op_lr, false);
-        phase_store_point(c, c.Ynew, c.snew, d.op_out_R, d.op_out_s);
+        (void)phase_model_retract(c, c.R(V_V), c.S(S_VS), d.op_lr, false);
+        phase_store_point(c, c.R(c.iYn), c.S(c.iSn), d.op_out_R, d.op_out_s);
         return;
     }
-    phase_operand_sR(c, c.Y, c.s);
+    phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
     XM_GSYNC(c);
     {
-        ObjArgs oa{c.Y, c.s, c.D};
-        double part = qy_phase<RP, NT, MODE_OBJ>(c, oa);
+        ObjArgs oa{c.R(c.iY), c.S(c.iS), c.R(c.iD)};
+        double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX, opcode == 3);
         c.publish(part); XM_GSYNC(c);
         const double f = c.collect();
         if (opcode == 1) { if (blockIdx.x == 0 && c.tid == 0) d.op_out_scalar[0] = f; return; }
@@ -440,7 +473,7 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const Dev d, const int op
         const double rd = c.collect();
         if (opcode == 2) {
             if (blockIdx.x == 0 && c.tid == 0) d.op_out_scalar[0] = sqrt(rd);
-            phase_store_point(c, d.RG, d.rgs, d.op_out_R, d.op_out_s);
+            phase_store_point(c, c.R(V_RG), c.S(S_RGS), d.op_out_R, d.op_out_s);
             return;
         }
     }
@@ -449,43 +482,28 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const Dev d, const int op
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double p[3] = {0, 0, 0}, y[3];
-        ld3(c.Y, i, d.r, c.j, act, y);
+        ld3(c.R(c.iY), i, d.r, c.j, act, y);
         if (act) {
             const double* pp = d.op_in_P + (size_t)c.j * d.n3 + 3 * i;
             p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
         }
-        st3(d.P, i, d.r, c.j, act, p);
-        const double si = valid ? c.s[i] : 0.0;
+        st3(c.R(V_P), i, d.r, c.j, act, p);
+        const double si = valid ? c.S(c.iS)[i] : 0.0;
         const double psi = (valid && i > 0) ? d.op_in_ps[i] : 0.0;
-        if (valid && c.j == 0) d.ps[i] = psi;
+        if (valid && c.j == 0) c.S(S_PS)[i] = psi;
         double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
         st_operand(d.Xt, d.ldq, i, c.j, act, x);
     }
     XM_GSYNC(c);
     {
         ObjArgs oa{nullptr, nullptr, nullptr};
-        (void)qy_phase<RP, NT, MODE_HESS>(c, oa);
-        phase_store_point(c, d.HP, d.hps, d.op_out_R, d.op_out_s);
+        (void)qy_phase<RP, NT, MODE_HESS, PATH>(c, oa, mapsQ.m, &mapX, false);
+        phase_store_point(c, c.R(V_HP), c.S(S_HPS), d.op_out_R, d.op_out_s);
     }
     return;
 xm_abort:
+    ring_drain(c);
     return;
-}
-
-// ------------------------------------------------------------------------------------------------ layout kernels
-// Qp[i*ldq + k] = Qcm[i + ld*k]  (column-major user matrix -> padded row-major), 32x32 smem tiles, pad stays zero
-__global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld, int n3, double* __restrict__ Qp, int ldq) {
-    __shared__ double tile[32][33];
-    const int bi = blockIdx.y * 32, bk = blockIdx.x * 32;
-    for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // read: consecutive threads along i (contiguous in col-major)
-        const int k = bk + t, i = bi + threadIdx.x;
-        tile[t][threadIdx.x] = (i < n3 && k < n3) ? Qcm[(size_t)i + (size_t)ld * k] : 0.0;
-    }
-    __syncthreads();
-    for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // write: consecutive threads along k
-        const int i = bi + t, k = bk + threadIdx.x;
-        if (i < n3 && k < ldq) Qp[(size_t)i * ldq + k] = (k < n3) ? tile[threadIdx.x][t] : 0.0;
-    }
 }
 
 }  // namespace xm
