@@ -14,11 +14,11 @@ R0 = xo.from_blocks(xo.identity_init(N, 3))
 h.trust_region(R0, np.ones(N), 0.0, 1e-6)
 res = h.trust_region(R0, np.ones(N), 0.0, 1e-6)
 st = res.stats
-print(json.dumps(dict(kc=os.environ.get("XM_TUNE_KC"), st=os.environ.get("XM_TUNE_ST"), nprod=os.environ.get("XM_TUNE_NPROD"), qy_free_us=free * 1e3, qy_lock_us=lock * 1e3,
+print(json.dumps(dict(kc=os.environ.get("XM_TUNE_KC"), st=os.environ.get("XM_TUNE_ST"), pf=os.environ.get("XM_TUNE_PF"), qy_free_us=free * 1e3, qy_lock_us=lock * 1e3,
       solve_ms=st["solve_ms"], qy_in_solve_us=st["qy_ms"] * 1e3 / st["qy_products"], sync_us=st["sync_ms"] * 1e3 / st["qy_products"],
       per_product_us=st["solve_ms"] * 1e3 / st["qy_products"], its=st["tcg_iters"])))
 '''
-for kc, stv, npd in [(128, 24, 1), (128, 24, 2), (128, 24, 4), (192, 24, 4), (192, 24, 2), (256, 24, 4), (64, 24, 4), (128, 24, 3)]:
-    env = dict(os.environ, XM_TUNE_KC=str(kc), XM_TUNE_ST=str(stv), XM_TUNE_NPROD=str(npd))
+for pf in [0, 2, 4, 6, 8, 12, 16, 24]:
+    env = dict(os.environ, XM_TUNE_PF=str(pf))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:], flush=True)

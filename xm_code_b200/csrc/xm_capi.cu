@@ -186,7 +186,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.cpw = 32 / p.W;
     p.NSW = p.NW * p.cpw;
     int G = h->opt.grid_ctas > 0 ? h->opt.grid_ctas : h->num_sm;
-    G = std::min(G, h->num_sm);
+    G = std::min(G, std::min(h->num_sm, 159));           // grid_sync() polls at most 5 slots per lane (G + 1 <= 160)
     G = std::max(1, std::min(G, h->N));
     p.G = G;
     const int cpc = (h->N + G - 1) / G;
@@ -195,9 +195,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     if (const char* e = getenv("XM_TUNE_NPROD")) { int v = atoi(e); if (p.use_tma && v >= 1 && v <= 4) p.nprod = v; }     // tuning hook
     const int nwork = p.NW - p.nprod;                   // warps that stream
     p.NWC = nwork;
-    p.KC = 192;     // measured (profiles/r01_sweep_ring*.txt): fewer, larger chunks win; 192 keeps >= 3 stages for r <= 8
-    if (const char* e = getenv("XM_TUNE_KC")) { int v = atoi(e); if (v >= 64 && v <= 256 && v % 64 == 0) p.KC = v; }   // tuning hook
-    if (allow_tma == 2) p.KC = 128;
+    p.KC = kKC;     // compile-time chunk width of the TMA ring (xm_device.cuh)
     p.nchunks = (h->ldq + p.KC - 1) / p.KC;
     // k-split: the largest divisor KS of nwork with KS * cpc <= nwork (or the caller's cap), at most one chunk/step each
     const int kmax = p.use_tma ? p.nchunks : (h->is_bsr ? nwork : std::max(1, h->ldq / 64));
@@ -214,11 +212,10 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
     if (p.use_tma) {
         p.nbmax = std::min(p.CB, cpc);
-        p.stage_doubles = (3 * p.nbmax + r) * p.KC;
+        p.stage_doubles = (3 * p.nbmax + p.RP) * p.KC;   // operand area sized for the padded rank (consumers read RP rows)
         int ST = (int)((budget - 1024) / ((size_t)p.stage_doubles * sizeof(double)));
         ST = std::min(ST, 24);
         if (const char* e = getenv("XM_TUNE_ST")) { int v = atoi(e); if (v >= 2) ST = std::min(ST, v); }                      // tuning hook
-        if (ST < 3 && p.KC > 128) return make_plan(h, r, 2);   // deep ring matters more than chunk width: retry with KC = 128
         if (ST < 2) return make_plan(h, r, 0);          // ring does not fit: direct streaming loads
         p.ST = ST;
         // batch heights that occur: CTAs own q or q+1 cameras; full batches have CB cameras, a CTA's last batch the rest
@@ -237,7 +234,7 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     const size_t N = h->N, n3 = h->n3, ldq = h->ldq;
     const size_t vecR = align_up(n3 * r * sizeof(double), 256), vecS = align_up(N * sizeof(double), 256);
     const size_t total = kNumVecR * vecR + align_up(N * 6 * sizeof(double), 256) + kNumVecS * vecS + align_up((size_t)r * ldq * sizeof(double), 256) +
-                         align_up((size_t)kPartialBufs * p.G * kPartialStride * sizeof(double), 256);
+                         align_up((size_t)kPartialBufs * (p.G + 1) * kPartialStride * sizeof(double), 256);
     bool fresh = false;
     if (h->ws_cap < total) {
         if (h->ws) cudaFree(h->ws);
@@ -263,6 +260,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;
     d.vec_smem = p.vec_smem; d.cpc_max = p.cpc; d.profile = h->opt.profile;
     d.nprod = p.nprod; d.NWC = p.NWC;
+    d.l2_prefetch = 0;     // measured: L2 prefetch shortens the Q.Y phase but lengthens the barriers by as much (profiles/r01_sweep_l2_prefetch.txt)
+    if (const char* e = getenv("XM_TUNE_PF")) d.l2_prefetch = std::max(0, atoi(e));          // tuning hook
     d.use_tma = p.use_tma; d.KC = p.KC; d.ST = p.ST; d.nbmax = p.nbmax; d.nchunks = p.nchunks; d.stage_doubles = p.stage_doubles;
     if (p.use_tma) {
         int rc = make_map(h, &h->mapX, d.Xt, (uint64_t)ldq, (uint64_t)r, (uint64_t)ldq, (uint32_t)p.KC, (uint32_t)r);

@@ -21,7 +21,8 @@ namespace xm {
 constexpr int kMaxRank = 20;
 constexpr int kLogCap = 1002;
 constexpr int kPartialBufs = 4;
-constexpr int kPartialStride = 2;   // doubles per CTA slot: [0] = partial sum, [1] = flag from CTA 0
+constexpr int kKC = 192;            // TMA ring: columns per chunk (box inner dimension, <= 256); see profiles/r01_sweep_ring_*.txt
+constexpr int kPartialStride = 1;   // doubles per slot; G slots for the CTA sums + 1 for CTA 0's flag, x kPartialBufs rotating buffers
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
 enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, kNumVecR };
@@ -49,6 +50,7 @@ struct Dev {
     int G, NW, KS, CB, W, cpw, NSW;
     // dense Q.Y through a shared-memory ring fed by 2-D tensor-map TMA (use_tma) or by direct streaming loads
     int use_tma, KC, ST, nbmax, nchunks, stage_doubles;
+    int l2_prefetch;           // Q chunks (beyond the ring) prefetched into L2 at the end of a Q.Y phase
     int nprod, NWC;            // TMA path: producer warps (the last nprod warps of the CTA) and consumer warps
     int box_nb[3];             // cameras per Q box of the three tensor maps (one TMA op moves a whole batch: 3*nb rows x KC)
     int op_repeat;             // xm_bench_qy: Q.Y phases per launch
@@ -126,6 +128,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(col0), "r"(row0), "r"(smem_u32(bar)) : "memory");
 }
+// explicit shared-window load (the ring pointer is generic; a generic LD costs more than LDS).  volatile: stays ordered
+// after the volatile mbarrier wait and before the volatile arrive.
+__device__ __forceinline__ double2 lds_v2(unsigned saddr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+    return v;
+}
+// fire-and-forget prefetch of one 2-D box into L2 (no shared-memory destination, no mbarrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int col0, int row0) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(col0), "r"(row0) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -180,41 +193,20 @@ struct Ctx {
         act = j < d.r;
         cam_lo = (int)(((long long)blockIdx.x * d.N) / d.G);
         cam_hi = (int)(((long long)(blockIdx.x + 1) * d.N) / d.G);
-        epoch = 0; pbuf = 0; aborted = false; t_qy = 0; t_sync = 0; dbg0 = dbg1 = dbg2 = dbg3 = 0; trace_n = 0; trace_on = false;
+        epoch = 0; pbuf = 0; aborted = false; pend_v = 0.0; pend_f = 0.0; t_qy = 0; t_sync = 0; dbg0 = dbg1 = dbg2 = dbg3 = 0; trace_n = 0; trace_on = false;
         red = red_; bsum = bsum_; bcast = bcast_;
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
         ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
     }
 
-    // ---- grid-wide barrier (all CTAs co-resident: cooperative launch).  Returns false if it timed out / aborted.
-    __device__ __forceinline__ bool grid_sync() {
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long t0 = gtimer();
-            epoch += 1;
-            const unsigned target = epoch * (unsigned)d.G;
-            __threadfence();
-            atomicAdd(d.bar, 1u);
-            int ok = 1;
-            unsigned spins = 0;
-#pragma unroll 1
-            while (ld_acquire_u32(d.bar) < target) {
-                if ((++spins & 0x3ffu) == 0) {
-                    if (*(volatile int*)d.abort_flag) { ok = 0; break; }
-                    if (gtimer() - t0 > 4000000000ull) { *(volatile int*)d.abort_flag = 1; ok = 0; break; }
-                }
-            }
-            __threadfence();
-            t_sync += gtimer() - t0;
-            bcast[3] = ok ? 1.0 : 0.0;
-        }
-        __syncthreads();
-        if (bcast[3] == 0.0) { aborted = true; return false; }
-        return true;
-    }
-
-    // ---- block reduction of one double per thread -> partials[pbuf][cta]; flag travels in slot [1] (CTA 0's counts)
+    // ---- grid-wide barrier fused with a deterministic all-reduce (all CTAs co-resident: cooperative launch).
+    // Arrival: release fence, this CTA's partial sum into its slot, one RED.add on a monotone counter.  Thread 0 spins on
+    // the counter (one hot line, 148 pollers); once it is complete warp 0 reads all slots (one more L2 round trip) and adds
+    // them in slot order: identical bits in every CTA, run to run.  (Measured alternatives — all-to-all slot polling with
+    // tagged values, with or without the counter — were slower: the polling traffic on ~20 hot lines outweighs the saved
+    // round trip; profiles/r01_barrier_variants.txt.)
+    double pend_v, pend_f;
     __device__ __forceinline__ void publish(double v, double flag = 0.0) {
         v = warpsum(v);
         if (lane == 0) bsum[warp] = v;
@@ -222,26 +214,64 @@ struct Ctx {
         if (tid == 0) {
             double t = 0.0;
             for (int w = 0; w < NWARPS; ++w) t += bsum[w];
-            double* slotp = d.partials + ((size_t)pbuf * d.G + blockIdx.x) * kPartialStride;
-            slotp[0] = t; slotp[1] = flag;
+            pend_v = t; pend_f = flag;
         }
-        // the following grid_sync() starts with __syncthreads and fences thread 0's stores
     }
-    // after grid_sync: every CTA sums the G partials in the same order -> identical bits everywhere
-    __device__ __forceinline__ double collect(double* flag_out = nullptr) {
-        if (warp == 0) {
-            const double* base = d.partials + (size_t)pbuf * d.G * kPartialStride;
-            double t = 0.0;
-            for (int c = lane; c < d.G; c += 32) t += __ldcg(base + (size_t)c * kPartialStride);
-            t = warpsum(t);
-            if (lane == 0) { bcast[0] = t; bcast[1] = __ldcg(base + 1); }
-        }
+    __device__ __forceinline__ bool grid_sync() {
         __syncthreads();
-        double t = bcast[0];
-        if (flag_out) *flag_out = bcast[1];
+        epoch += 1;                                           // uniform in every thread of every CTA
+        if (warp == 0) {
+            unsigned long long t0 = 0;
+            if (tid == 0) t0 = gtimer();
+            double* slots = d.partials + (size_t)pbuf * (d.G + 1);
+            const unsigned target = epoch * (unsigned)d.G;
+            int ok = 1;
+            if (tid == 0) {
+                slots[blockIdx.x] = pend_v;
+                if (blockIdx.x == 0) slots[d.G] = pend_f;                   // CTA 0's flag rides in the extra slot G
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");            // release everything this CTA wrote
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(d.bar) : "memory");
+                pend_v = 0.0; pend_f = 0.0;
+                unsigned spins = 0;
+#pragma unroll 1
+                while (ld_acquire_u32(d.bar) < target) {
+                    if ((++spins & 0x3ffu) == 0) {
+                        if (*(volatile int*)d.abort_flag) { ok = 0; break; }
+                        if (gtimer() - t0 > 4000000000ull) { *(volatile int*)d.abort_flag = 1; ok = 0; break; }
+                    }
+                }
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");            // acquire
+            }
+            __syncwarp();
+            constexpr int MAXS = 5;                                          // G + 1 <= 160 slots -> at most 5 per lane
+            double w[MAXS];
+#pragma unroll
+            for (int q = 0; q < MAXS; ++q) {                                 // independent loads: one L2 round trip
+                const int sl = lane + 32 * q;
+                w[q] = (sl <= d.G) ? __ldcg(slots + sl) : 0.0;
+            }
+            double acc = 0.0, f0 = 0.0;
+#pragma unroll
+            for (int q = 0; q < MAXS; ++q) {                                 // fixed slot order per lane
+                const int sl = lane + 32 * q;
+                if (sl < d.G) acc += w[q];
+                if (sl == d.G) f0 = w[q];
+            }
+            acc = warpsum(acc);
+            f0 = warpsum(f0);                                                // exactly one lane holds the flag, the rest add 0
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (lane == 0) { bcast[0] = acc; bcast[1] = f0; bcast[3] = ok ? 1.0 : 0.0; }
+            if (tid == 0) t_sync += gtimer() - t0;
+        }
         __syncthreads();
         pbuf = (pbuf + 1) % kPartialBufs;
-        return t;
+        if (bcast[3] == 0.0) { aborted = true; return false; }
+        return true;
+    }
+    // the sum (and CTA 0's flag) gathered by the last grid_sync(); identical bits in every CTA
+    __device__ __forceinline__ double collect(double* flag_out = nullptr) {
+        if (flag_out) *flag_out = bcast[1];
+        return bcast[0];
     }
 };
 
@@ -493,7 +523,8 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
                                                bool prefetch_next) {
     const Dev& d = c.d;
     const int NWC = d.NWC, nprod = d.nprod;
-    const int KS = d.KS, CB = d.CB, KC = d.KC, ST = d.ST, nchunks = d.nchunks;
+    const int KS = d.KS, CB = d.CB, ST = d.ST, nchunks = d.nchunks;
+    constexpr int KC = kKC;
     const int ncam = c.cam_hi - c.cam_lo;
     const int nbatches = (ncam + CB - 1) / CB;
     const int uses = nbatches * nchunks;
@@ -539,11 +570,26 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
                 tma_load_2d(st + xoff, mapX, ch * KC, 0, &c.fullX[s]);
             }
         }
+        // Beyond the ring: pull the next chunks of Q into L2 while the CTA sits in the per-camera phases and grid barriers
+        // (HBM would otherwise idle there; the ring alone holds only ~12% of this CTA's rows).
+        if (ok && prefetch_next && c.lane == 0 && pw == 0) {
+            for (int uu = npre; uu < npre + d.l2_prefetch && uu < uses; ++uu) {
+                const int bi = uu / nchunks, ch = uu - bi * nchunks;
+                const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
+                const CUtensorMap* mq = (nb == d.box_nb[0]) ? mapQ3 : (nb == d.box_nb[1]) ? mapQ3 + 1 : mapQ3 + 2;
+                tma_prefetch_l2_2d(mq, ch * KC, 3 * b0);
+            }
+        }
         if (!ok && c.lane == 0) *(volatile int*)d.abort_flag = 1;
     } else {
         // ------------------------------------------------ consumers
         const int cslot = c.warp / KS, ks = c.warp % KS;
+        const unsigned ring_s = smem_u32(c.ring);
+        const unsigned stage_bytes = (unsigned)(stage_doubles * sizeof(double));
+        const unsigned row_bytes = (unsigned)(KC * sizeof(double));
         bool ok = true;
+        int chk = (int)((g0 % (unsigned)KS));                // chunk -> k-split owner by running counter (no modulo per chunk)
+        (void)chk;
         for (int bi = 0; bi < nbatches && ok; ++bi) {
             const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
             const bool has = cslot < nb;
@@ -552,6 +598,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
+            int own = 0;                                     // own == ks  <=>  ch % KS == ks
             for (int ch = 0; ch < nchunks; ++ch) {
                 const unsigned g = g0 + bi * nchunks + ch;
                 const int s = g % ST; const unsigned par = (g / ST) & 1;
@@ -560,25 +607,29 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
                 if (!mbar_wait(&c.fullQ[s], par) || !mbar_wait(&c.fullX[s], par)) { ok = false; break; }
                 c.tr(100 + ch);
                 unsigned long long tw1 = 0; if (tm) { tw1 = gtimer(); if (bi == 0 && ch == 0) c.dbg0 += tw1 - tw0; else c.dbg1 += tw1 - tw0; }
-                if (has && (ch % KS) == ks) {
-                    const double* st = c.ring + (size_t)s * stage_doubles;
-                    const double* q0 = st + (size_t)(3 * cslot) * KC;
-                    const double* xs = st + xoff;
-                    for (int k = 2 * c.lane; k < KC; k += 64) {
-                        const double2 a0 = *reinterpret_cast<const double2*>(q0 + k);
-                        const double2 a1 = *reinterpret_cast<const double2*>(q0 + KC + k);
-                        const double2 a2 = *reinterpret_cast<const double2*>(q0 + 2 * KC + k);
+                if (has && own == ks) {
+                    const unsigned q0 = ring_s + (unsigned)s * stage_bytes + (unsigned)(3 * cslot) * row_bytes + (unsigned)(2 * c.lane) * 8u;
+                    const unsigned xs = ring_s + (unsigned)s * stage_bytes + (unsigned)(xoff * sizeof(double)) + (unsigned)(2 * c.lane) * 8u;
+                    // All RP operand columns are processed without predicates: for r < RP the extra rows of the stage's operand
+                    // area hold stale (in-bounds) data and feed accumulators nobody reads.  Loads first, then the FMAs.
 #pragma unroll
-                        for (int jj = 0; jj < RP; ++jj) {
-                            if (jj < d.r) {
-                                const double2 x = *reinterpret_cast<const double2*>(xs + (size_t)jj * KC + k);
-                                acc[0][jj] = fma(a0.x, x.x, acc[0][jj]); acc[0][jj] = fma(a0.y, x.y, acc[0][jj]);
-                                acc[1][jj] = fma(a1.x, x.x, acc[1][jj]); acc[1][jj] = fma(a1.y, x.y, acc[1][jj]);
-                                acc[2][jj] = fma(a2.x, x.x, acc[2][jj]); acc[2][jj] = fma(a2.y, x.y, acc[2][jj]);
-                            }
-                        }
+                    for (int k0 = 0; k0 < kKC; k0 += 64) {
+                        double2 a[3], x[RP];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) a[q] = lds_v2(q0 + (unsigned)q * row_bytes + k0 * 8);
+#pragma unroll
+                        for (int jj = 0; jj < RP; ++jj) x[jj] = lds_v2(xs + (unsigned)jj * row_bytes + k0 * 8);
+#pragma unroll
+                        for (int jj = 0; jj < RP; ++jj)
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) acc[q][jj] = fma(a[q].x, x[jj].x, acc[q][jj]);
+#pragma unroll
+                        for (int jj = 0; jj < RP; ++jj)
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) acc[q][jj] = fma(a[q].y, x[jj].y, acc[q][jj]);
                     }
                 }
+                if (++own == KS) own = 0;
                 __syncwarp();
                 if (c.lane == 0) mbar_arrive(&c.empty[s]);
                 if (tm) c.dbg2 += gtimer() - tw1;
