@@ -1,10 +1,15 @@
 #!/usr/bin/env python
 """bench.py — XM Burer-Monteiro trust-region throughput on B200 (driver contract in the task statement).
 
-Workload (N=1): BAL-Ladybug-1723-shaped synthetic dense Q (1723 cameras, 3N = 5169, Q = 213.7 MB FP64 > L2), one
+Workload: BAL-Ladybug-1723-shaped synthetic dense Q (1723 cameras, 3N = 5169, Q = 213.7 MB FP64 > L2), one
 "step" = one full XMtrustregion-equivalent call at rank 3 from the reference's identity start to gradnorm < 1e-6
 (reference call: XMtrustregion(C,R0,s0,R,s,lam=0,gradtol=1e-6,ls=0,...), XM/include/XM/trustregion.h:77).
 metric = tCG iterations per second (each iteration = one Q.Y + the fused per-camera work), time-to-KKT = ms_per_step.
+
+--gpus N > 1 (torchrun, one process per GPU): the SAME solve partitioned by camera over the N GPUs ("scaling":
+"strong") — rank k holds the rows of Q of its cameras; per tCG iteration the persistent kernels exchange the operand
+rows and the reduction scalars by peer-mapped stores over NVLink (xm_code_b200/dist.py, include/xm_b200.h).
+XM_BENCH_CAMERAS=<n> changes the camera count (e.g. 13682 = BAL-Final-sized dense Q, 13.5 GB).
 
   value : device-resident (Q, R0, s0 already in HBM; CUDA events on the launch stream)
   e2e   : through the C-ABI with HOST buffers — xm_set_q_dense (pinned H2D of Q + re-layout) + xm_trust_region
@@ -112,7 +117,7 @@ def oracle_sample(Q, seconds):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from xm_code_b200 import capi
+    from xm_code_b200 import capi, dist as xdist
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -124,6 +129,10 @@ def run_ours(args):
     N = N_CAMERAS; n3 = 3 * N
     h = capi.Handle(device=local, profile=bool(int(os.environ.get("XM_PROFILE", "0"))), qy_variant=int(os.environ.get("XM_QY_VARIANT", "0")),
                     vec_in_global=bool(int(os.environ.get("XM_VEC_GLOBAL", "0"))))
+    cam_lo, cam_hi = 0, N
+    if world > 1:        # one solve, cameras (rows of Q) partitioned over the ranks; torch.distributed only carries the IPC handles
+        info = xdist.attach(h, N, RANK)
+        cam_lo, cam_hi = info["cam_lo"], info["cam_hi"]
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
     # host (pinned) and device copies of the inputs, wire layout (column-major)
@@ -144,7 +153,7 @@ def run_ours(args):
         return primal, st
 
     def step_e2e():
-        h.set_q_dense_ptr(n3, Q_pin.data_ptr(), n3)
+        h.set_q_dense_ptr(n3, Q_pin.data_ptr(), n3)             # a rank of a communicator copies only its own rows
         gt = capi.C.c_double(GRADTOL); pr = capi.C.c_double(); st = capi.XmStats()
         rc = h.lib.xm_trust_region(h._h, RANK, capi.C.c_void_p(R0_pin.data_ptr()), capi.C.c_void_p(s0_pin.data_ptr()), LAM, capi.C.byref(gt),
                                    0.0, None, 1000.0, capi.C.c_void_p(R_out.data_ptr()), capi.C.c_void_p(s_out.data_ptr()),
@@ -183,57 +192,76 @@ def run_ours(args):
     ms_dev, it_dev, (primal, st) = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     ms_e2e, it_e2e, (primal_e, st_e) = timed(step_e2e, args.steps, max(1, args.warmup // 2))
-    # roofline of the dominant kernel phase: the dense Q.Y, timed alone
+    # roofline of the dominant kernel phase: the dense Q.Y, timed alone (collective calls when world > 1)
     X_dev = torch.randn(RANK, n3, dtype=torch.float64, device="cuda"); O_dev = torch.empty_like(X_dev)
     h.qy_dev(RANK, X_dev.data_ptr(), O_dev.data_ptr())
     qy_ms = h.bench_qy(RANK, 50)                 # 50 products inside one launch, free-running CTAs
     qy_ms_lockstep = h.bench_qy(RANK, -50)       # same with a grid barrier after every product (the solver's regime)
     barrier_us = h.bench_barrier(RANK, 2000)
-    alg_bytes = 72.0 * N * N + 48.0 * N * RANK
+    solve_ms = st["solve_ms"]
+    if world > 1:        # the slowest rank's kernel time counts
+        t = torch.tensor([solve_ms, qy_ms, qy_ms_lockstep, barrier_us], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        solve_ms, qy_ms, qy_ms_lockstep, barrier_us = (float(x) for x in t.tolist())
+    # algorithmic bytes of one Q.Y product ON ONE GPU: its rows of Q once, the operand once, its rows of the result once
+    rows_max = 3 * max(hi - lo for lo, hi in xdist.partition_table(N, world, st["grid_ctas"])) if world > 1 else n3
+    alg_bytes = 8.0 * rows_max * n3 + 8.0 * n3 * RANK + 8.0 * rows_max * RANK
     peak, peak_src = measured_peak_gbs()
+    if world > 1:
+        xdist.detach(h)
     if rank != 0:
         return
-    value = world * it_dev / (ms_dev * 1e-3)
-    e2e_value = world * it_e2e / (ms_e2e * 1e-3)
-    cpu_its, cpu_dt, cpu_res = oracle_sample(Qh, args.cpu_seconds)
+    # ONE solve shared by all ranks: the job's iterations are the solve's iterations (strong scaling for world > 1)
+    value = it_dev / (ms_dev * 1e-3)
+    e2e_value = it_e2e / (ms_e2e * 1e-3)
+    cpu_base = None
+    if world == 1:
+        cpu_its, cpu_dt, cpu_res = oracle_sample(Qh, args.cpu_seconds)
+        cpu_base = {"value": cpu_its, "unit": "tCG iterations/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"NumPy oracle (OpenBLAS dgemm Q.Y) on the same Q for {cpu_dt:.1f} s ({cpu_res.tcg_iters} tCG iterations, {cpu_res.outer_iters} outer)"}
     per_solve = it_dev / args.steps
+    slab_mb = 8.0 * rows_max * n3 / 1e6
+    achieved = alg_bytes * st["qy_products"] / (solve_ms * 1e-3) / 1e9
     line = {
         "metric": "xm_tcg_iterations_per_sec", "value": value, "unit": "tCG iterations/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "cameras": N, "rank": RANK, "gradtol": GRADTOL, "lam": LAM,
                    "tcg_iters_per_solve": per_solve, "outer_iters_per_solve": st["outer_iters"], "qy_products_per_solve": st["qy_products"],
                    "time_to_kkt_ms": ms_dev / args.steps, "final_objective": primal, "final_gradnorm": st["gradnorm"], "exit": st["exit"],
-                   "l2": "inputs larger than L2 (Q = %.1f MB vs 126 MB L2)" % (alg_bytes / 1e6),
+                   "l2": ("inputs larger than L2 (Q = %.1f MB vs 126 MB L2)" % slab_mb) if slab_mb > 126 else
+                         ("per-GPU slab of Q = %.1f MB fits the 126 MB L2: after the first product Q.Y streams from L2, the HBM roofline does not bound it" % slab_mb),
                    "grid_ctas": st["grid_ctas"], "threads_per_cta": st["threads_per_cta"], "ksplit": st["ksplit"],
-                   "in_kernel_ms": {"solve": st["solve_ms"], "qy": st["qy_ms"], "grid_sync_wait": st["sync_ms"],
+                   "in_kernel_ms": {"solve": solve_ms, "qy": st["qy_ms"], "grid_sync_wait": st["sync_ms"],
                                     "qy_first_tile_wait": st["phase_ms"][0], "qy_tile_waits": st["phase_ms"][1], "qy_tile_math": st["phase_ms"][2],
                                     "qy_reduce_epilogue": st["phase_ms"][3], "profile_timers_on": bool(int(os.environ.get("XM_PROFILE", "0")))},
                    "grid_barrier_us": barrier_us,
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas of the same solve (no collective; camera-partitioned solve is a later row)"},
+                   "parallelism": "single GPU" if world == 1 else
+                       f"one solve, cameras partitioned over {world} GPUs (rank 0 owns cameras [{cam_lo},{cam_hi})); per tCG iteration: operand rows "
+                       f"+ 2 reduction scalars + 3 barriers exchanged by peer-mapped stores from inside the persistent kernels (no NCCL on the path)"},
         "e2e": {"value": e2e_value, "unit": "tCG iterations/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(8 * (n3 * n3 + n3 * RANK + N)), "d2h_bytes_per_step": int(8 * (n3 * RANK + N))},
-        "gpu_launches": int(args.steps),   # one persistent solve kernel per step (e2e adds one re-layout kernel per step)
+                "h2d_bytes_per_step": int(8 * (n3 * n3 + world * (n3 * RANK + N))), "d2h_bytes_per_step": int(world * 8 * (n3 * RANK + N))},
+        "gpu_launches": int(args.steps) * world,   # one persistent solve kernel per rank per step (e2e adds one re-layout kernel per step)
         # dominant kernel = the persistent solve kernel (96.6 % of the step in profiles/r01_ncu_solve_and_launches.txt): one launch
-        # executes qy_products dense Q.Y products; algorithmic bytes per product = 72 N^2 + 48 N r
-        "roofline": {"bound": "hbm", "kernel": "xm_solve_kernel<3,512,0> (persistent: whole XMtrustregion call, Q.Y through the 2-D TMA ring)",
-                     "achieved": alg_bytes * st["qy_products"] / (st["solve_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_bytes * st["qy_products"] / (st["solve_ms"] * 1e-3) / 1e9 / peak,
-                     "traffic": NCU_SOLVE_DRAM_BYTES_PER_PRODUCT * st["qy_products"],
+        # executes qy_products dense Q.Y products; algorithmic bytes per product (per GPU) = 8 rows 3N + 8 (3N + rows) r
+        "roofline": {"bound": "hbm", "kernel": "xm_solve_kernel<3,512,0> (persistent: whole XMtrustregion call, Q.Y through the 2-D TMA ring)"
+                                               + ("" if world == 1 else " — per GPU, slowest rank"),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_SOLVE_DRAM_BYTES_PER_PRODUCT * st["qy_products"] if (world == 1 and N == 1723) else None,
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one solve launch (profiles/r01_ncu_solve_and_launches.txt), per product",
                      "algorithmic_bytes": alg_bytes * st["qy_products"], "algorithmic_bytes_per_product": alg_bytes,
-                     "ms_per_launch": st["solve_ms"], "products_per_launch": st["qy_products"], "peak_source": peak_src,
+                     "ms_per_launch": solve_ms, "products_per_launch": st["qy_products"], "peak_source": peak_src,
                      "qy_phase_alone": {"kernel": "xm_ops_kernel<3,512,0> (same qy_phase device code, MODE_OUT)",
                                         "us_per_product_free_running": qy_ms * 1e3, "us_per_product_lockstep": qy_ms_lockstep * 1e3,
                                         "achieved_lockstep": alg_bytes / (qy_ms_lockstep * 1e-3) / 1e9,
                                         "frac_lockstep": alg_bytes / (qy_ms_lockstep * 1e-3) / 1e9 / peak,
                                         "note": "50 products inside one launch; 'lockstep' adds a grid barrier after every product like the solver; "
-                                                "values above 1.0 of the measured copy peak come from read-only streaming plus a few % L2 hits on the re-read Q; "
+                                                "values above 1.0 of the measured copy peak come from read-only streaming plus L2 hits on the re-read Q; "
                                                 "a single cold product under ncu: 38.9 us, dram read 214.56 MB (profiles/r01_qy_tma_full.summary.txt)"}},
-        "cpu_baseline": {"value": cpu_its, "unit": "tCG iterations/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"NumPy oracle (OpenBLAS dgemm Q.Y) on the same Q for {cpu_dt:.1f} s ({cpu_res.tcg_iters} tCG iterations, {cpu_res.outer_iters} outer)"},
         "clocks": clocks,
     }
+    if cpu_base:
+        line["cpu_baseline"] = cpu_base
     print(json.dumps(line))
 
 

@@ -101,6 +101,31 @@ int  xm_set_q_dense_dev(xm_handle* h, int n3, const double* q_colmajor_dev, int6
 /* Block-CSR Q with bdim x bdim blocks (bdim in {3,4}); nb block rows; block values column-major per block. */
 int  xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, const int* colidx, const double* vals);
 
+/* ---- multi-GPU: one solve partitioned by camera over `world` <= 8 GPUs of one NVSwitch node (the
+ * reference is single-GPU, XM/include/Utils/memory.h:284,366).  Rank k owns a contiguous camera range (xm_partition) and
+ * holds only those rows of Q; per tCG iteration the persistent kernels exchange the Q.Y operand rows and one double per
+ * CTA per reduction by peer-mapped stores over NVLink — no host or NCCL call on the path.
+ * Protocol (every rank): xm_create -> xm_comm_init -> exchange the 64-byte handles (any transport, e.g. a
+ * torch.distributed all_gather) -> xm_comm_connect -> xm_set_q_* -> xm_trust_region* / xm_qy* / xm_op_*.  Every compute
+ * call is COLLECTIVE: all ranks make the same call with the same (full-size) vector arguments; every rank receives the
+ * full result.  xm_set_q_dense / xm_set_q_bsr given the whole matrix upload only the rank's rows; xm_set_q_dense_slab
+ * takes the rank's row slab alone.  xm_certify is single-GPU only (XM_EUNSUPPORTED on a communicator). */
+#define XM_IPC_HANDLE_BYTES 64
+#define XM_MAX_WORLD 8
+/* cameras [cam_lo, cam_hi) of `rank` when each of `world` ranks runs ctas_per_rank CTAs (pure host function, no GPU) */
+int  xm_partition(int n_cameras, int world, int ctas_per_rank, int rank, int* cam_lo, int* cam_hi);
+int  xm_comm_init(xm_handle* h, int rank, int world, int n_cameras, int max_r, unsigned char* ipc_handle_out /* 64 B or NULL */);
+int  xm_comm_connect(xm_handle* h, const unsigned char* all_handles /* world x 64 B, rank order (one process per GPU) */);
+int  xm_comm_connect_ptrs(xm_handle* h, void* const* arena_ptrs /* world pointers, rank order (one process, many GPUs) */);
+int  xm_comm_disconnect(xm_handle* h);  /* unmap the peers' arenas; every rank calls it (then a host barrier) before any xm_destroy */
+void* xm_comm_arena(xm_handle* h);
+int  xm_comm_info(const xm_handle* h, int* rank, int* world, int* ctas_per_rank, int* cam_lo, int* cam_hi);
+int  xm_comm_reset(xm_handle* h);   /* after XM_ESYNC; host-side barrier across ranks required before and after */
+/* Rows [row0, row0 + nrows) of Q only: q_slab points at element (row0, 0) of a column-major matrix with leading dimension
+ * ld >= nrows (ld = n3 when it is a view into the full matrix).  Must equal the rank's range 3*cam_lo .. 3*cam_hi. */
+int  xm_set_q_dense_slab(xm_handle* h, int n3, int row0, int nrows, const double* q_slab, int64_t ld);
+int  xm_set_q_dense_slab_dev(xm_handle* h, int n3, int row0, int nrows, const double* q_slab_dev, int64_t ld);
+
 /* out = alpha * Q * X ; X, out: 3N x r column-major (ld = 3N). */
 int  xm_qy(xm_handle* h, int r, double alpha, const double* X, double* out);
 int  xm_qy_dev(xm_handle* h, int r, double alpha, const double* X_dev, double* out_dev);

@@ -1,0 +1,224 @@
+"""GPU parity of the camera-partitioned (multi-GPU) solve against the oracle, through the C-ABI.
+
+Runs in two set-ups with the same assertions:
+  * `python -m pytest tests/test_gpu_multi.py -m gpu` on a box with >= 2 GPUs: ONE process, one handle per GPU connected
+    with xm_comm_connect_ptrs, the collective calls issued from one thread per handle;
+  * `torchrun --nproc-per-node W -m pytest tests/test_gpu_multi.py -m gpu`: one process per GPU, arenas exchanged as
+    CUDA-IPC handles through torch.distributed (the bench.py set-up); every rank runs the same tests in lock-step.
+Skipped on a single-GPU box (the driver's -m gpu run): the single-GPU tests cover the same device code with world == 1.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from oracle import xm_oracle as xo
+from conftest import anchored_gram
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1e-300, np.max(np.abs(b))))
+
+
+class Team:
+    """W handles sharing one communicator; call(name, *args) issues the collective on every local member."""
+
+    def __init__(self, n_cameras, max_r, **opts):
+        import torch
+        from xm_code_b200 import capi, dist as xdist
+        self.torchrun = int(os.environ.get("WORLD_SIZE", "1")) > 1
+        if self.torchrun:
+            import torch.distributed as dist
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.world = dist.get_world_size()
+            h = capi.Handle(device=local, **opts)
+            xdist.attach(h, n_cameras, max_r)
+            self.handles = [h]
+        else:
+            self.world = min(torch.cuda.device_count(), int(os.environ.get("XM_TEST_WORLD", "2")))
+            self.handles = [capi.Handle(device=k, **opts) for k in range(self.world)]
+            for k, h in enumerate(self.handles):
+                h.comm_init(k, self.world, n_cameras, max_r)
+            ptrs = [h.comm_arena() for h in self.handles]
+            for h in self.handles:
+                h.comm_connect_ptrs(ptrs)
+            self.pool = ThreadPoolExecutor(self.world)
+
+    def call(self, name, *args, **kw):
+        if len(self.handles) == 1:
+            return [getattr(self.handles[0], name)(*args, **kw)]
+        futs = [self.pool.submit(getattr(h, name), *args, **kw) for h in self.handles]
+        return [f.result(timeout=300) for f in futs]
+
+    def close(self):
+        for h in self.handles:            # importers unmap first, then the arenas are freed
+            h.comm_disconnect()
+        if self.torchrun:
+            import torch.distributed as dist
+            dist.barrier()
+        for h in self.handles:
+            h.close()
+
+
+@pytest.fixture
+def team_factory():
+    import torch
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (or torchrun)")
+    made = []
+
+    def make(n_cameras, max_r, **opts):
+        t = Team(n_cameras, max_r, **opts)
+        made.append(t)
+        return t
+    yield make
+    for t in made:
+        t.close()
+
+
+def rand_psd(n3, rng):
+    A = rng.standard_normal((n3, n3 + 3))
+    return A @ A.T / n3
+
+
+def rand_point(N, r, rng):
+    Y = xo.mgs_rows(rng.standard_normal((N, 3, r)))
+    s = np.concatenate([[1.0], rng.uniform(0.7, 1.4, N - 1)])
+    return Y, s
+
+
+def test_partition_and_barrier(team_factory):
+    t = team_factory(500, 3)
+    infos = t.call("comm_info")
+    for i in infos:
+        assert i["world"] == t.world and 0 <= i["cam_lo"] < i["cam_hi"] <= 500
+    rng = np.random.default_rng(0)
+    Q = rand_psd(1500, rng)
+    t.call("set_q_dense", Q)
+    us = t.call("bench_barrier", 3, 500)
+    assert all(0.5 < u < 100.0 for u in us), us
+
+
+@pytest.mark.parametrize("N,r,opts", [(300, 3, {}), (301, 5, {}), (700, 10, {}), (97, 4, dict(grid_ctas=5)),
+                                       (640, 3, dict(qy_variant=1)), (333, 13, {}), (2000, 3, dict(vec_in_global=True))])
+def test_qy_dense_matches_oracle(team_factory, N, r, opts):
+    rng = np.random.default_rng(100 + N + r)
+    Q = rand_psd(3 * N, rng) + 0.1 * rng.standard_normal((3 * N, 3 * N))     # not symmetric: out = Q X
+    t = team_factory(N, r, **opts)
+    t.call("set_q_dense", Q)
+    X = rng.standard_normal((3 * N, r))
+    for got in t.call("qy", X, 2.0):                 # every rank receives the full product
+        assert rel(got, 2.0 * Q @ X) < TOL
+    for got in t.call("qy", -X, 1.0):                # second launch on the same communicator (epoch carries over)
+        assert rel(got, -Q @ X) < TOL
+
+
+def test_qy_bsr_matches_dense(team_factory):
+    from xm_code_b200 import problems
+    rowptr, col, vals = problems.erdos_renyi_bsr(400, avg_degree=12, seed=4)
+    Q = problems.bsr_to_dense(rowptr, col, vals)
+    rng = np.random.default_rng(3)
+    t = team_factory(400, 10)
+    t.call("set_q_bsr", rowptr, col, vals, 3)
+    for r in (3, 10):
+        X = rng.standard_normal((1200, r))
+        for got in t.call("qy", X, 0.5):
+            assert rel(got, 0.5 * Q @ X) < TOL
+
+
+@pytest.mark.parametrize("N,r,lam", [(64, 5, 0.0), (333, 3, 0.1), (600, 8, 0.0)])
+def test_objective_gradient_hessian_retraction(team_factory, N, r, lam):
+    rng = np.random.default_rng(200 + N + r)
+    Q = rand_psd(3 * N, rng)
+    Y, s = rand_point(N, r, rng)
+    R = xo.from_blocks(Y)
+    t = team_factory(N, r)
+    t.call("set_q_dense", Q)
+    fref = xo.objective(Q, Y, s, lam)
+    for f in t.call("objective", R, s, lam):
+        assert abs(f - fref) < TOL * 10 * abs(fref)
+    D, G, g = xo.egrad(Q, Y, s, lam)
+    rgR, rgs = xo.project(Y, s, G, g)
+    for gR, gs, gn in t.call("rgrad", R, s, lam):
+        assert rel(gR, xo.from_blocks(rgR)) < TOL * 10 and rel(gs, rgs) < TOL * 10
+    P = rng.standard_normal(Y.shape); ps = rng.standard_normal(N); ps[0] = 0.0
+    HR, Hs = xo.rhess_vec(Q, Y, s, lam, D, G, g, P, ps)
+    for gHR, gHs in t.call("rhess", R, s, xo.from_blocks(P), ps, lam):
+        assert rel(gHR, xo.from_blocks(HR)) < TOL * 10 and rel(gHs, Hs) < TOL * 10
+    eta = 0.3 * rng.standard_normal(Y.shape); es = 0.2 * rng.standard_normal(N)
+    Yn, sn = xo.retract(Y, s, eta, es, 0.7)
+    for gRn, gsn in t.call("retract", R, s, xo.from_blocks(eta), es, 0.7):
+        assert rel(gRn, xo.from_blocks(Yn)) < TOL * 10 and rel(gsn, sn) < TOL * 10
+
+
+def check_point(got, ref, primal_rel=1e-9, s_abs=1e-7, x_abs=1e-6):
+    assert abs(got.primal - ref.primal) <= primal_rel * abs(ref.primal)
+    np.testing.assert_allclose(got.s, ref.s, atol=s_abs, rtol=0)
+    np.testing.assert_allclose(anchored_gram(got.R, got.s), anchored_gram(xo.from_blocks(ref.Y), ref.s), atol=x_abs, rtol=0)
+
+
+def test_solve_simple1_matches_oracle_on_every_rank(team_factory, simple1_q):
+    N = simple1_q.shape[0] // 3
+    t = team_factory(N, 3)
+    t.call("set_q_dense", simple1_q)
+    ref = xo.trust_region(simple1_q, xo.identity_init(N, 3), np.ones(N), 0.0, 1e-16)
+    res = t.call("trust_region", xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.0, 1e-16)
+    for got in res:
+        assert abs(got.primal - 2.550991567720) < 5e-11          # certified global optimum
+        check_point(got, ref, primal_rel=1e-10, s_abs=1e-8, x_abs=1e-7)
+        assert got.stats["outer_iters"] == ref.outer_iters
+    if len(res) > 1:       # identical control flow and identical bits on all ranks
+        assert res[0].stats["tcg_iters"] == res[1].stats["tcg_iters"] and res[0].primal == res[1].primal
+        np.testing.assert_array_equal(res[0].R, res[1].R)
+    # and again on the same communicator (counters and epoch persist across launches)
+    for got in t.call("trust_region", xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.0, 1e-16):
+        assert got.primal == res[0].primal
+
+
+@pytest.mark.parametrize("opts", [{}, dict(vec_in_global=True), dict(qy_variant=1)])
+def test_solve_synthetic_with_regulariser(team_factory, opts):
+    from xm_code_b200 import problems
+    N = 400
+    Q, _ = problems.synthetic_dense_q(N, seed=5)
+    ref = xo.trust_region(Q, xo.identity_init(N, 3), np.ones(N), 0.05, 1e-8)
+    t = team_factory(N, 3, **opts)
+    t.call("set_q_dense", Q)
+    for got in t.call("trust_region", xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.05, 1e-8):
+        check_point(got, ref)
+
+
+def test_rank_escalation_line_search_path(team_factory):
+    rng = np.random.default_rng(11)
+    N = 60
+    A = rng.standard_normal((3 * N, 3 * N + 2))
+    Q = A @ A.T / (3 * N)
+    res3 = xo.trust_region(Q, xo.identity_init(N, 3), np.ones(N), 0.0, 1e-7)
+    c = xo.certificate(Q, xo.from_blocks(res3.Y * res3.s[:, None, None]), 0.0, res3.primal)
+    assert not c["certified"]
+    Y0 = np.concatenate([res3.Y, np.zeros((N, 3, 1))], axis=2)
+    v = (c["v"].reshape(N, 3) / res3.s[:, None]).reshape(-1)
+    ref = xo.trust_region(Q, Y0, res3.s, 0.0, 1e-7, ls_step=1.0, v=v)
+    t = team_factory(N, 4)
+    t.call("set_q_dense", Q)
+    for got in t.call("trust_region", xo.from_blocks(Y0), res3.s, 0.0, 1e-7, ls_step=1.0, v=v):
+        assert got.primal < res3.primal
+        check_point(got, ref, primal_rel=1e-8, s_abs=1e-6, x_abs=1e-5)
+
+
+def test_certify_is_refused_on_a_communicator(team_factory):
+    from xm_code_b200 import capi
+    rng = np.random.default_rng(1)
+    N = 50
+    Q = rand_psd(150, rng)
+    Y, s = rand_point(N, 3, rng)
+    t = team_factory(N, 3)
+    t.call("set_q_dense", Q)
+    with pytest.raises(capi.XmError):
+        t.handles[0].certify(xo.from_blocks(Y), s, 0.0, 1.0)

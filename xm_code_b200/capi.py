@@ -42,7 +42,11 @@ EXPORTS = [
     "xm_set_q_dense_dev", "xm_set_q_bsr", "xm_qy", "xm_qy_dev", "xm_trust_region", "xm_trust_region_dev",
     "xm_op_objective", "xm_op_rgrad", "xm_op_rhess", "xm_op_retract", "xm_certify", "xm_escape_scale", "xm_bench_qy",
     "xm_bench_barrier", "xm_debug_trace",
+    "xm_partition", "xm_comm_init", "xm_comm_connect", "xm_comm_connect_ptrs", "xm_comm_arena", "xm_comm_info", "xm_comm_reset", "xm_comm_disconnect",
+    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev",
 ]
+XM_IPC_HANDLE_BYTES = 64
+XM_MAX_WORLD = 8
 
 _lib = None
 
@@ -83,9 +87,21 @@ def load(path: str | None = None):
     lib.xm_bench_qy.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.xm_bench_barrier.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.xm_debug_trace.argtypes = [vp, vp]
+    ip = C.POINTER(C.c_int)
+    lib.xm_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+    lib.xm_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.xm_comm_connect.argtypes = [vp, vp]
+    lib.xm_comm_connect_ptrs.argtypes = [vp, C.POINTER(vp)]
+    lib.xm_comm_arena.argtypes = [vp]
+    lib.xm_comm_arena.restype = vp
+    lib.xm_comm_info.argtypes = [vp, ip, ip, ip, ip, ip]
+    lib.xm_comm_reset.argtypes = [vp]
+    lib.xm_comm_disconnect.argtypes = [vp]
+    lib.xm_set_q_dense_slab.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
+    lib.xm_set_q_dense_slab_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("xm_default_options", "xm_last_error"):
+        if name not in ("xm_default_options", "xm_last_error", "xm_comm_arena"):
             fn.restype = C.c_int
     if path is None:
         _lib = lib
@@ -94,6 +110,16 @@ def load(path: str | None = None):
 
 class XmError(RuntimeError):
     pass
+
+
+def partition(n_cameras: int, world: int, ctas_per_rank: int, rank: int):
+    """Cameras [lo, hi) owned by `rank` (pure host arithmetic in the library; works without a GPU)."""
+    lib = load()
+    lo, hi = C.c_int(), C.c_int()
+    rc = lib.xm_partition(n_cameras, world, ctas_per_rank, rank, C.byref(lo), C.byref(hi))
+    if rc != 0:
+        raise XmError(f"xm_partition: {ERRORS.get(rc, rc)}")
+    return lo.value, hi.value
 
 
 def _f64(a, order="F"):
@@ -148,6 +174,42 @@ class Handle:
         if rc != 0:
             msg = self.lib.xm_last_error(self._h)
             raise XmError(f"{what}: {ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    # ---- multi-GPU communicator (camera partition; include/xm_b200.h "multi-GPU")
+    def comm_init(self, rank: int, world: int, n_cameras: int, max_r: int = 5) -> bytes:
+        buf = (C.c_ubyte * XM_IPC_HANDLE_BYTES)()
+        self._check(self.lib.xm_comm_init(self._h, rank, world, n_cameras, max_r, C.cast(buf, C.c_void_p)), "xm_comm_init")
+        return bytes(buf)
+
+    def comm_connect(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.xm_comm_connect(self._h, C.cast(buf, C.c_void_p)), "xm_comm_connect")
+
+    def comm_connect_ptrs(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._check(self.lib.xm_comm_connect_ptrs(self._h, arr), "xm_comm_connect_ptrs")
+
+    def comm_arena(self) -> int:
+        return int(self.lib.xm_comm_arena(self._h) or 0)
+
+    def comm_info(self) -> dict:
+        v = [C.c_int() for _ in range(5)]
+        self._check(self.lib.xm_comm_info(self._h, *[C.byref(x) for x in v]), "xm_comm_info")
+        return dict(zip(("rank", "world", "ctas_per_rank", "cam_lo", "cam_hi"), (x.value for x in v)))
+
+    def comm_disconnect(self):
+        self._check(self.lib.xm_comm_disconnect(self._h), "xm_comm_disconnect")
+
+    def comm_reset(self):
+        self._check(self.lib.xm_comm_reset(self._h), "xm_comm_reset")
+
+    def set_q_dense_slab(self, Q_slab, row0: int):
+        """Q_slab: this rank's rows of Q, shape (nrows, 3N)."""
+        Q_slab = _f64(Q_slab)
+        nrows, n3 = Q_slab.shape
+        self._check(self.lib.xm_set_q_dense_slab(self._h, n3, row0, nrows, _ptr(Q_slab), nrows), "xm_set_q_dense_slab")
+        self.N = n3 // 3
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.xm_set_stream(self._h, C.c_void_p(cuda_stream)), "xm_set_stream")

@@ -15,21 +15,24 @@ using namespace xm;
 namespace xm {
 // ------------------------------------------------------------------------------------------------ layout kernels
 // Qp[i*ldq + k] = Qcm[i + ld*k]  (column-major user matrix -> padded row-major), 32x32 smem tiles, pad stays zero
-__global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld, int n3, double* __restrict__ Qp, int ldq) {
+// (Qcm points at the first of `nrows` rows of the n3-column matrix: a rank's slab when the cameras are partitioned)
+__global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld, int nrows, int n3, double* __restrict__ Qp, int ldq) {
     __shared__ double tile[32][33];
     const int bi = blockIdx.y * 32, bk = blockIdx.x * 32;
     for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // read: consecutive threads along i (contiguous in col-major)
         const int k = bk + t, i = bi + threadIdx.x;
-        tile[t][threadIdx.x] = (i < n3 && k < n3) ? Qcm[(size_t)i + (size_t)ld * k] : 0.0;
+        tile[t][threadIdx.x] = (i < nrows && k < n3) ? Qcm[(size_t)i + (size_t)ld * k] : 0.0;
     }
     __syncthreads();
     for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // write: consecutive threads along k
         const int i = bi + t, k = bk + threadIdx.x;
-        if (i < n3 && k < ldq) Qp[(size_t)i * ldq + k] = (k < n3) ? tile[threadIdx.x][t] : 0.0;
+        if (i < nrows && k < ldq) Qp[(size_t)i * ldq + k] = (k < n3) ? tile[threadIdx.x][t] : 0.0;
     }
 }
 
 }  // namespace xm
+
+static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static_assert(sizeof(xm_log_rec) == sizeof(LogRec), "log record layout");
 static_assert(XM_LOG_CAP == kLogCap, "log cap");
@@ -75,6 +78,7 @@ extern "C" int xm_create(xm_handle** out, const xm_options* opt) {
               cudaMallocHost(&h->h_stats, sizeof(DevStats)) == cudaSuccess &&
               cudaMallocHost(&h->h_log, sizeof(LogRec) * kLogCap) == cudaSuccess;
     if (!ok) { xm_destroy(h); return XM_ENOMEM; }
+    cudaMemset(h->d_bar, 0, 256); cudaMemset(h->d_abort, 0, 256);
     *out = h;
     return XM_OK;
 }
@@ -86,6 +90,9 @@ extern "C" int xm_destroy(xm_handle* h) {
     cudaFree(h->ws); cudaFree(h->d_stats); cudaFree(h->d_log); cudaFree(h->d_bar); cudaFree(h->d_abort); cudaFree(h->d_scalar);
     cudaFree(h->io_R0); cudaFree(h->io_s0); cudaFree(h->io_v); cudaFree(h->io_Rout); cudaFree(h->io_sout); cudaFree(h->io_P); cudaFree(h->io_ps);
     cudaFreeHost(h->h_stats); cudaFreeHost(h->h_log);
+    for (int w = 0; w < kMaxWorld; ++w) if (h->peer_ipc[w] && h->peer_arena[w]) cudaIpcCloseMemHandle(h->peer_arena[w]);
+    cudaFree(h->arena);
+    cudaGetLastError();
     delete h;
     return XM_OK;
 }
@@ -93,6 +100,133 @@ extern "C" int xm_destroy(xm_handle* h) {
 extern "C" int xm_set_stream(xm_handle* h, void* s) {
     if (!h) return XM_EINVAL;
     h->stream = (cudaStream_t)s;
+    return XM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU communicator
+// Camera partition of SURVEY.md §8e.  The job runs on world * G CTAs; global CTA g owns the cameras [g N / GT, (g+1) N / GT),
+// so rank k (CTAs [kG, (k+1)G)) owns the contiguous range below and holds exactly those rows of Q.
+extern "C" int xm_partition(int n_cameras, int world, int ctas_per_rank, int rank, int* cam_lo, int* cam_hi) {
+    if (n_cameras <= 0 || world < 1 || world > kMaxWorld || ctas_per_rank < 1 || rank < 0 || rank >= world) return XM_EINVAL;
+    const long long GT = (long long)world * ctas_per_rank;
+    if (cam_lo) *cam_lo = (int)(((long long)rank * ctas_per_rank * n_cameras) / GT);
+    if (cam_hi) *cam_hi = (int)(((long long)(rank + 1) * ctas_per_rank * n_cameras) / GT);
+    return XM_OK;
+}
+
+extern "C" int xm_comm_init(xm_handle* h, int rank, int world, int n_cameras, int max_r, unsigned char* ipc_handle_out) {
+    if (!h) return XM_EINVAL;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_cameras < world || max_r < 3 || max_r > XM_MAX_RANK) {
+        h->err = "xm_comm_init: bad rank/world/camera count/max rank"; return XM_EINVAL;
+    }
+    if (h->arena) { h->err = "communicator already initialised on this handle"; return XM_EINVAL; }
+    XM_CUDA(h, cudaSetDevice(h->device));
+    int G = h->opt.grid_ctas > 0 ? h->opt.grid_ctas : h->num_sm;
+    G = std::max(1, std::min(std::min(G, h->num_sm), n_cameras / world));
+    const int GT = G * world;
+    const size_t n3 = 3 * (size_t)n_cameras, ldq = (n3 + 63) / 64 * 64;
+    size_t off = 0;
+    h->off_bar = off; off += 256;
+    h->off_abort = off; off += 256;
+    h->off_partials = off; off += align_up_sz((size_t)kPartialBufs * (GT + 1) * kPartialStride * sizeof(double), 256);
+    h->off_xt = off; off += align_up_sz((size_t)max_r * ldq * sizeof(double), 256);
+    h->off_outR = off; off += align_up_sz(n3 * max_r * sizeof(double), 256);
+    h->off_outS = off; off += align_up_sz((size_t)n_cameras * sizeof(double), 256);
+    if (cudaMalloc(&h->arena, off) != cudaSuccess) { cudaGetLastError(); h->arena = nullptr; h->err = "communicator arena cudaMalloc failed"; return XM_ENOMEM; }
+    h->arena_bytes = off;
+    XM_CUDA(h, cudaMemset(h->arena, 0, off));
+    XM_CUDA(h, cudaMemset(h->d_bar, 0, 256));
+    XM_CUDA(h, cudaDeviceSynchronize());
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == XM_IPC_HANDLE_BYTES, "ipc handle size");
+        cudaIpcMemHandle_t mh;
+        XM_CUDA(h, cudaIpcGetMemHandle(&mh, h->arena));
+        memcpy(ipc_handle_out, &mh, sizeof(mh));
+    }
+    h->world = world; h->rank = rank; h->comm_G = G; h->comm_N = n_cameras; h->comm_maxr = max_r;
+    h->comm_connected = (world == 1); h->comm_broken = false;
+    for (int w = 0; w < kMaxWorld; ++w) { h->peer_arena[w] = nullptr; h->peer_ipc[w] = false; }
+    h->peer_arena[rank] = h->arena;
+    xm_partition(n_cameras, world, G, rank, &h->cam0, &h->cam1);
+    // an operator uploaded before the communicator existed covers the wrong rows
+    h->N = 0; h->n3 = 0;
+    return XM_OK;
+}
+
+// one process per GPU: `all_handles` = the world x 64-byte handles returned by xm_comm_init on every rank, in rank order
+extern "C" int xm_comm_connect(xm_handle* h, const unsigned char* all_handles) {
+    if (!h || !all_handles || !h->arena) return XM_EINVAL;
+    XM_CUDA(h, cudaSetDevice(h->device));
+    for (int w = 0; w < h->world; ++w) {
+        if (w == h->rank) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, all_handles + (size_t)w * XM_IPC_HANDLE_BYTES, sizeof(mh));
+        void* p = nullptr;
+        XM_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_arena[w] = (char*)p; h->peer_ipc[w] = true;
+    }
+    h->comm_connected = true;
+    return XM_OK;
+}
+
+// one process driving several GPUs: `arena_ptrs` = xm_comm_arena() of every rank's handle, in rank order
+extern "C" int xm_comm_connect_ptrs(xm_handle* h, void* const* arena_ptrs) {
+    if (!h || !arena_ptrs || !h->arena) return XM_EINVAL;
+    XM_CUDA(h, cudaSetDevice(h->device));
+    for (int w = 0; w < h->world; ++w) {
+        if (w == h->rank) continue;
+        cudaPointerAttributes at;
+        XM_CUDA(h, cudaPointerGetAttributes(&at, arena_ptrs[w]));
+        int can = 0;
+        XM_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, at.device));
+        if (!can) { h->err = "no peer access between the communicator's devices"; return XM_EUNSUPPORTED; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return XM_ECUDA; }
+        cudaGetLastError();
+        h->peer_arena[w] = (char*)arena_ptrs[w];
+    }
+    h->comm_connected = true;
+    return XM_OK;
+}
+
+// Unmap the peers' arenas (before any rank frees its own: the importer must close first).  Collective by convention:
+// every rank disconnects, the ranks meet at a host barrier, then handles may be destroyed.
+extern "C" int xm_comm_disconnect(xm_handle* h) {
+    if (!h) return XM_EINVAL;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int w = 0; w < kMaxWorld; ++w) {
+        if (h->peer_ipc[w] && h->peer_arena[w]) cudaIpcCloseMemHandle(h->peer_arena[w]);
+        if (w != h->rank) h->peer_arena[w] = nullptr;
+        h->peer_ipc[w] = false;
+    }
+    cudaGetLastError();
+    if (h->world > 1) h->comm_connected = false;
+    return XM_OK;
+}
+
+extern "C" void* xm_comm_arena(xm_handle* h) { return h ? (void*)h->arena : nullptr; }
+
+extern "C" int xm_comm_info(const xm_handle* h, int* rank, int* world, int* ctas_per_rank, int* cam_lo, int* cam_hi) {
+    if (!h) return XM_EINVAL;
+    if (rank) *rank = h->rank;
+    if (world) *world = h->world;
+    if (ctas_per_rank) *ctas_per_rank = h->comm_G;
+    if (cam_lo) *cam_lo = h->cam0;
+    if (cam_hi) *cam_hi = h->cam1;
+    return XM_OK;
+}
+
+// After XM_ESYNC the ranks' barrier epochs may differ.  Call on EVERY rank, with a host-side barrier across the ranks
+// before (no kernel in flight anywhere) and after (nobody launches into a counter that is about to be zeroed).
+extern "C" int xm_comm_reset(xm_handle* h) {
+    if (!h || !h->arena) return XM_EINVAL;
+    XM_CUDA(h, cudaSetDevice(h->device));
+    XM_CUDA(h, cudaDeviceSynchronize());
+    XM_CUDA(h, cudaMemset(h->arena, 0, h->off_xt));          // counter, abort flag, reduction slots
+    XM_CUDA(h, cudaMemset(h->d_bar, 0, 256));
+    XM_CUDA(h, cudaDeviceSynchronize());
+    h->comm_broken = false;
     return XM_OK;
 }
 
@@ -105,56 +239,87 @@ static int ensure(xm_handle* h, double** p, size_t* cap, size_t bytes) {
     return XM_OK;
 }
 
-static int set_q_common(xm_handle* h, int n3, const double* q, int64_t ld, bool from_device) {
-    if (!h || !q || n3 <= 0 || n3 % 3 != 0 || ld < n3) return XM_EINVAL;
+// rows of the operator this handle keeps: everything, or the slab of its cameras once a communicator is attached
+static void owned_cameras(const xm_handle* h, int N, int* c0, int* c1) {
+    if (h->world > 1) { *c0 = h->cam0; *c1 = h->cam1; } else { *c0 = 0; *c1 = N; }
+}
+
+// q_slab: first element of row `row0` of the column-major n3-column matrix (leading dimension ld), nrows rows
+static int set_q_common(xm_handle* h, int n3, int row0, int nrows, const double* q_slab, int64_t ld, bool from_device) {
+    if (!h || !q_slab || n3 <= 0 || n3 % 3 != 0 || ld < nrows || nrows <= 0) return XM_EINVAL;
+    if (h->world > 1 && h->comm_N * 3 != n3) { h->err = "Q size differs from the communicator's camera count"; return XM_EINVAL; }
+    int c0, c1;
+    owned_cameras(h, n3 / 3, &c0, &c1);
+    if (row0 != 3 * c0 || nrows != 3 * (c1 - c0)) { h->err = "row slab does not match this rank's camera range"; return XM_EINVAL; }
     XM_CUDA(h, cudaSetDevice(h->device));
     const int ldq = (n3 + 63) / 64 * 64;
-    int rc = ensure(h, &h->Qp, &h->Qp_cap, (size_t)n3 * ldq * sizeof(double));
+    int rc = ensure(h, &h->Qp, &h->Qp_cap, (size_t)nrows * ldq * sizeof(double));
     if (rc) return rc;
-    const double* src = q;
+    const double* src = q_slab;
     if (!from_device) {
-        rc = ensure(h, &h->Qstage, &h->Qstage_cap, (size_t)n3 * n3 * sizeof(double));
+        rc = ensure(h, &h->Qstage, &h->Qstage_cap, (size_t)nrows * n3 * sizeof(double));
         if (rc) return rc;
-        XM_CUDA(h, cudaMemcpy2DAsync(h->Qstage, (size_t)n3 * sizeof(double), q, (size_t)ld * sizeof(double),
-                                     (size_t)n3 * sizeof(double), n3, cudaMemcpyHostToDevice, h->stream));
-        src = h->Qstage; ld = n3;
+        XM_CUDA(h, cudaMemcpy2DAsync(h->Qstage, (size_t)nrows * sizeof(double), q_slab, (size_t)ld * sizeof(double),
+                                     (size_t)nrows * sizeof(double), n3, cudaMemcpyHostToDevice, h->stream));
+        src = h->Qstage; ld = nrows;
     }
-    dim3 blk(32, 8), grd((ldq + 31) / 32, (n3 + 31) / 32);
-    xm_repack_q_kernel<<<grd, blk, 0, h->stream>>>(src, (long long)ld, n3, h->Qp, ldq);
+    dim3 blk(32, 8), grd((ldq + 31) / 32, (nrows + 31) / 32);
+    xm_repack_q_kernel<<<grd, blk, 0, h->stream>>>(src, (long long)ld, nrows, n3, h->Qp, ldq);
     XM_CUDA(h, cudaGetLastError());
     h->launches++;
     h->n3 = n3; h->N = n3 / 3; h->ldq = ldq; h->is_bsr = false;
+    h->cam0 = c0; h->cam1 = c1;
     return XM_OK;
 }
-extern "C" int xm_set_q_dense(xm_handle* h, int n3, const double* q, int64_t ld) { return set_q_common(h, n3, q, ld, false); }
-extern "C" int xm_set_q_dense_dev(xm_handle* h, int n3, const double* q, int64_t ld) { return set_q_common(h, n3, q, ld, true); }
+// full matrix given: a rank of a communicator uploads only the rows of its own cameras
+static int set_q_full(xm_handle* h, int n3, const double* q, int64_t ld, bool from_device) {
+    if (!h || !q || n3 <= 0 || n3 % 3 != 0 || ld < n3) return XM_EINVAL;
+    int c0, c1;
+    owned_cameras(h, n3 / 3, &c0, &c1);
+    return set_q_common(h, n3, 3 * c0, 3 * (c1 - c0), q + 3 * c0, ld, from_device);
+}
+extern "C" int xm_set_q_dense(xm_handle* h, int n3, const double* q, int64_t ld) { return set_q_full(h, n3, q, ld, false); }
+extern "C" int xm_set_q_dense_dev(xm_handle* h, int n3, const double* q, int64_t ld) { return set_q_full(h, n3, q, ld, true); }
+extern "C" int xm_set_q_dense_slab(xm_handle* h, int n3, int row0, int nrows, const double* q_slab, int64_t ld) {
+    return set_q_common(h, n3, row0, nrows, q_slab, ld, false);
+}
+extern "C" int xm_set_q_dense_slab_dev(xm_handle* h, int n3, int row0, int nrows, const double* q_slab, int64_t ld) {
+    return set_q_common(h, n3, row0, nrows, q_slab, ld, true);
+}
 
 extern "C" int xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, const int* colidx, const double* vals) {
     if (!h || !rowptr || !colidx || !vals || nb <= 0 || (bdim != 3 && bdim != 4)) return XM_EINVAL;
+    if (h->world > 1 && h->comm_N != nb) { h->err = "Q size differs from the communicator's camera count"; return XM_EINVAL; }
     XM_CUDA(h, cudaSetDevice(h->device));
-    const int nnzb = rowptr[nb];
+    // a rank of a communicator keeps only the block rows of its own cameras (the caller passes the whole matrix)
+    int c0, c1;
+    owned_cameras(h, nb, &c0, &c1);
+    const long long bb0 = rowptr[c0], nnzb = (long long)rowptr[c1] - bb0;
+    std::vector<int> rp((size_t)(c1 - c0) + 1);
+    for (int i = c0; i <= c1; ++i) rp[i - c0] = (int)(rowptr[i] - bb0);
     // re-block on the host into 4x4 row-major padded blocks (128 B each); for bdim==4 only the leading 3x3 acts on
     // the rotation rows (the 4th row/col belongs to translations, which the BM path has already eliminated).
     std::vector<double> blk((size_t)nnzb * 16, 0.0);
-    for (int b = 0; b < nnzb; ++b)
+    for (long long b = 0; b < nnzb; ++b)
         for (int cc = 0; cc < bdim; ++cc)
             for (int rr = 0; rr < bdim; ++rr)
-                blk[(size_t)b * 16 + rr * 4 + cc] = vals[(size_t)b * bdim * bdim + (size_t)cc * bdim + rr];
+                blk[(size_t)b * 16 + rr * 4 + cc] = vals[(size_t)(bb0 + b) * bdim * bdim + (size_t)cc * bdim + rr];
     cudaFree(h->bsr_rowptr); cudaFree(h->bsr_col); cudaFree(h->bsr_val);
     h->bsr_rowptr = nullptr; h->bsr_col = nullptr; h->bsr_val = nullptr;
-    XM_CUDA(h, cudaMalloc(&h->bsr_rowptr, sizeof(int) * (nb + 1)));
-    XM_CUDA(h, cudaMalloc(&h->bsr_col, sizeof(int) * std::max(nnzb, 1)));
-    XM_CUDA(h, cudaMalloc(&h->bsr_val, sizeof(double) * 16 * std::max(nnzb, 1)));
-    XM_CUDA(h, cudaMemcpy(h->bsr_rowptr, rowptr, sizeof(int) * (nb + 1), cudaMemcpyHostToDevice));
-    XM_CUDA(h, cudaMemcpy(h->bsr_col, colidx, sizeof(int) * nnzb, cudaMemcpyHostToDevice));
+    XM_CUDA(h, cudaMalloc(&h->bsr_rowptr, sizeof(int) * rp.size()));
+    XM_CUDA(h, cudaMalloc(&h->bsr_col, sizeof(int) * std::max(nnzb, 1LL)));
+    XM_CUDA(h, cudaMalloc(&h->bsr_val, sizeof(double) * 16 * std::max(nnzb, 1LL)));
+    XM_CUDA(h, cudaMemcpy(h->bsr_rowptr, rp.data(), sizeof(int) * rp.size(), cudaMemcpyHostToDevice));
+    XM_CUDA(h, cudaMemcpy(h->bsr_col, colidx + bb0, sizeof(int) * nnzb, cudaMemcpyHostToDevice));
     XM_CUDA(h, cudaMemcpy(h->bsr_val, blk.data(), sizeof(double) * 16 * nnzb, cudaMemcpyHostToDevice));
     h->bsr_bdim = bdim; h->is_bsr = true;
     h->N = nb; h->n3 = 3 * nb; h->ldq = (h->n3 + 63) / 64 * 64;
+    h->cam0 = c0; h->cam1 = c1;
     return XM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ launch planning
-struct Plan { int RP, NT, NW, W, cpw, NSW, G, KS, CB; int use_tma, KC, ST, nbmax, nchunks, stage_doubles; int box_nb[3]; size_t dyn_smem; int vec_smem, cpc; size_t vec_bytes; int nprod, NWC; };
+struct Plan { int RP, NT, NW, W, cpw, NSW, G, GT, KS, CB; int use_tma, KC, ST, nbmax, nchunks, stage_doubles; int box_nb[3]; size_t dyn_smem; int vec_smem, cpc; size_t vec_bytes; int nprod, NWC; };
 
 static int rank_pad(int r) {
     static const int pads[] = {3, 4, 5, 6, 8, 10, 12, 16, 20};
@@ -186,10 +351,12 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.cpw = 32 / p.W;
     p.NSW = p.NW * p.cpw;
     int G = h->opt.grid_ctas > 0 ? h->opt.grid_ctas : h->num_sm;
-    G = std::min(G, std::min(h->num_sm, 159));           // grid_sync() polls at most 5 slots per lane (G + 1 <= 160)
+    G = std::min(G, h->num_sm);                          // cooperative launch: one CTA per SM
     G = std::max(1, std::min(G, h->N));
+    if (h->world > 1) G = h->comm_G;                     // fixed when the communicator was created (identical on every rank)
     p.G = G;
-    const int cpc = (h->N + G - 1) / G;
+    const int GT = G * h->world;                         // CTAs of the whole job: cameras are dealt out over all of them
+    const int cpc = (h->N + GT - 1) / GT;
     p.use_tma = (allow_tma && !h->is_bsr && h->opt.qy_variant != 1 && h->encode_tiled) ? 1 : 0;
     p.nprod = p.use_tma ? 1 : 0;                        // TMA path: the last nprod warps are producers (1 suffices)
     if (const char* e = getenv("XM_TUNE_NPROD")) { int v = atoi(e); if (p.use_tma && v >= 1 && v <= 4) p.nprod = v; }     // tuning hook
@@ -203,7 +370,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     for (int k = 1; k <= nwork; ++k)
         if (nwork % k == 0 && k <= kmax && ((h->opt.ksplit > 0) ? (k <= h->opt.ksplit) : (k * cpc <= nwork))) KS = k;
     p.KS = KS; p.CB = nwork / KS;
-    p.cpc = cpc;
+    p.cpc = cpc; p.GT = GT;
     // per-CTA state vectors in shared memory when they are small (kills the L2 round trips of every per-camera phase)
     size_t budget = (size_t)std::min(h->smem_optin, 227 * 1024) - 12 * 1024;               // static smem + slack
     p.vec_bytes = (((size_t)(kNumVecR * 3 * r + kNumVecS + 6) * cpc * sizeof(double)) + 127) / 128 * 128;
@@ -220,21 +387,21 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
         p.ST = ST;
         // batch heights that occur: CTAs own q or q+1 cameras; full batches have CB cameras, a CTA's last batch the rest
         auto last = [&](int n) { return n <= 0 ? p.CB : n - ((n - 1) / p.CB) * p.CB; };
-        const int q = h->N / G;
+        const int q = h->N / GT;
         p.box_nb[0] = std::min(p.CB, cpc); p.box_nb[1] = last(q); p.box_nb[2] = last(q + 1);
         p.dyn_smem += (size_t)ST * p.stage_doubles * sizeof(double) + 3 * ST * sizeof(unsigned long long);
     }
     return p;
 }
 
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static size_t align_up(size_t x, size_t a) { return align_up_sz(x, a); }
 
 // carve the workspace for (N, r, G); zero it when the geometry changed (operand pad rows must be zero)
 static int carve(xm_handle* h, int r, const Plan& p) {
     const size_t N = h->N, n3 = h->n3, ldq = h->ldq;
     const size_t vecR = align_up(n3 * r * sizeof(double), 256), vecS = align_up(N * sizeof(double), 256);
     const size_t total = kNumVecR * vecR + align_up(N * 6 * sizeof(double), 256) + kNumVecS * vecS + align_up((size_t)r * ldq * sizeof(double), 256) +
-                         align_up((size_t)kPartialBufs * (p.G + 1) * kPartialStride * sizeof(double), 256);
+                         align_up((size_t)kPartialBufs * (p.GT + 1) * kPartialStride * sizeof(double), 256);
     bool fresh = false;
     if (h->ws_cap < total) {
         if (h->ws) cudaFree(h->ws);
@@ -242,9 +409,9 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         if (cudaMalloc(&h->ws, total) != cudaSuccess) { cudaGetLastError(); h->err = "workspace cudaMalloc failed"; return XM_ENOMEM; }
         h->ws_cap = total; fresh = true;
     }
-    if (fresh || h->ws_r != r || h->ws_N != (int)N || h->ws_G != p.G || h->ws_ldq != (int)ldq) {
+    if (fresh || h->ws_r != r || h->ws_N != (int)N || h->ws_G != p.GT || h->ws_ldq != (int)ldq) {
         XM_CUDA(h, cudaMemsetAsync(h->ws, 0, total, h->stream));
-        h->ws_r = r; h->ws_N = (int)N; h->ws_G = p.G; h->ws_ldq = (int)ldq;
+        h->ws_r = r; h->ws_N = (int)N; h->ws_G = p.GT; h->ws_ldq = (int)ldq;
     }
     char* q = h->ws;
     Dev& d = h->dev;
@@ -258,6 +425,18 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.Q = h->is_bsr ? nullptr : h->Qp;
     d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim;
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;
+    d.rank = h->rank; d.world = h->world; d.GT = p.GT; d.g0 = h->rank * p.G; d.cam0 = h->cam0; d.row0 = 3 * h->cam0;
+    d.bar = h->d_bar; d.abort_flag = h->d_abort; d.epoch_store = h->d_bar + 16;
+    if (h->world > 1) {       // exchange buffers live in the peer-mapped arenas (same layout on every rank)
+        d.Xt = (double*)(h->arena + h->off_xt); d.partials = (double*)(h->arena + h->off_partials);
+        d.bar = (unsigned long long*)(h->arena + h->off_bar); d.abort_flag = (int*)(h->arena + h->off_abort);
+        for (int w = 0; w < h->world; ++w) {
+            d.Xt_peer[w] = (double*)(h->peer_arena[w] + h->off_xt); d.partials_peer[w] = (double*)(h->peer_arena[w] + h->off_partials);
+            d.bar_peer[w] = (unsigned long long*)(h->peer_arena[w] + h->off_bar); d.abort_peer[w] = (int*)(h->peer_arena[w] + h->off_abort);
+        }
+    } else {
+        d.Xt_peer[0] = d.Xt; d.partials_peer[0] = d.partials; d.bar_peer[0] = d.bar; d.abort_peer[0] = d.abort_flag;
+    }
     d.vec_smem = p.vec_smem; d.cpc_max = p.cpc; d.profile = h->opt.profile;
     d.nprod = p.nprod; d.NWC = p.NWC;
     d.l2_prefetch = 0;     // measured: L2 prefetch shortens the Q.Y phase but lengthens the barriers by as much (profiles/r01_sweep_l2_prefetch.txt)
@@ -267,12 +446,12 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         int rc = make_map(h, &h->mapX, d.Xt, (uint64_t)ldq, (uint64_t)r, (uint64_t)ldq, (uint32_t)p.KC, (uint32_t)r);
         if (rc) return rc;
         for (int t = 0; t < 3; ++t) {
-            rc = make_map(h, &h->mapQ[t], h->Qp, (uint64_t)ldq, (uint64_t)n3, (uint64_t)ldq, (uint32_t)p.KC, (uint32_t)(3 * p.box_nb[t]));
+            rc = make_map(h, &h->mapQ[t], h->Qp, (uint64_t)ldq, (uint64_t)(3 * (h->cam1 - h->cam0)), (uint64_t)ldq, (uint32_t)p.KC, (uint32_t)(3 * p.box_nb[t]));
             if (rc) return rc;
             d.box_nb[t] = p.box_nb[t];
         }
     }
-    d.bar = h->d_bar; d.abort_flag = h->d_abort; d.stats = h->d_stats; d.log = h->d_log;
+    d.stats = h->d_stats; d.log = h->d_log;
     d.op_out_scalar = h->d_scalar;
     d.op_repeat = 1;
     d.replicate_stale_sr = h->opt.replicate_stale_sr; d.max_outer = h->opt.max_outer; d.max_inner = h->opt.max_inner;
@@ -314,23 +493,42 @@ static int prepare(xm_handle* h, int r, Plan* plan) {
     if (!h) return XM_EINVAL;
     if (r < 3 || r > XM_MAX_RANK) { h->err = "rank out of range [3,20]"; return XM_EINVAL; }
     if (h->N <= 0 || (!h->is_bsr && !h->Qp)) { h->err = "no Q set"; return XM_EINVAL; }
+    if (h->world > 1) {
+        if (!h->comm_connected) { h->err = "communicator not connected (xm_comm_connect)"; return XM_EINVAL; }
+        if (h->comm_broken) { h->err = "communicator desynchronised by an earlier abort (xm_comm_reset on every rank)"; return XM_ESYNC; }
+        if (h->N != h->comm_N || r > h->comm_maxr) { h->err = "problem does not fit the communicator (camera count / max rank)"; return XM_EINVAL; }
+    }
     XM_CUDA(h, cudaSetDevice(h->device));
     *plan = make_plan(h, r);
     int rc = carve(h, r, *plan);
     if (rc) return rc;
     rc = ensure_io(h, r);
     if (rc) { h->err = "io staging alloc failed"; return rc; }
-    XM_CUDA(h, cudaMemsetAsync(h->d_bar, 0, 256, h->stream));
-    XM_CUDA(h, cudaMemsetAsync(h->d_abort, 0, 256, h->stream));
+    if (h->world == 1) {      // with a communicator the counters are monotone across launches: a peer may already be arriving
+        XM_CUDA(h, cudaMemsetAsync(h->d_bar, 0, 256, h->stream));
+        XM_CUDA(h, cudaMemsetAsync(h->d_abort, 0, 256, h->stream));
+    }
     return XM_OK;
 }
 
 static int check_abort(xm_handle* h) {
     int ab = 0;
-    XM_CUDA(h, cudaMemcpyAsync(&ab, h->d_abort, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    const int* flag = h->world > 1 ? (const int*)(h->arena + h->off_abort) : h->d_abort;
+    XM_CUDA(h, cudaMemcpyAsync(&ab, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     XM_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (ab) { h->err = "device grid barrier timed out"; return XM_ESYNC; }
+    if (ab) { h->err = "device grid barrier timed out"; if (h->world > 1) h->comm_broken = true; return XM_ESYNC; }
     return XM_OK;
+}
+
+// Where a launch leaves its results on THIS device.  Single GPU: straight into the caller's / staging buffers.  With a
+// communicator every CTA stores its cameras into every rank's arena copy; the caller's buffer is filled from the local copy.
+struct OutBind { double* R; double* s; };
+static OutBind bind_out(xm_handle* h, Dev& d, double* R_dev, double* s_dev) {
+    if (h->world == 1) { d.outR_peer[0] = R_dev; d.outS_peer[0] = s_dev; return {R_dev, s_dev}; }
+    for (int w = 0; w < h->world; ++w) {
+        d.outR_peer[w] = (double*)(h->peer_arena[w] + h->off_outR); d.outS_peer[w] = (double*)(h->peer_arena[w] + h->off_outS);
+    }
+    return {(double*)(h->arena + h->off_outR), (double*)(h->arena + h->off_outS)};
 }
 
 // ------------------------------------------------------------------------------------------------ Q.Y
@@ -345,13 +543,12 @@ static int qy_common(xm_handle* h, int r, double alpha, const double* X, double*
     XM_CUDA(h, cudaMemcpy2DAsync(d.Xt, (size_t)d.ldq * sizeof(double), X, (size_t)d.n3 * sizeof(double),
                                  (size_t)d.n3 * sizeof(double), r, kin, h->stream));
     d.qy_alpha = alpha;
-    d.op_out_R = dev_ptrs ? out : h->io_Rout;
+    const OutBind ob = bind_out(h, d, dev_ptrs ? out : h->io_Rout, h->io_sout);
     XM_CUDA(h, launch_ops(h, d, 0, p, h->stream));
     h->launches++;
-    if (!dev_ptrs) {
-        XM_CUDA(h, cudaMemcpyAsync(out, h->io_Rout, (size_t)d.n3 * r * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        XM_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
+    if (!dev_ptrs || ob.R != out)
+        XM_CUDA(h, cudaMemcpyAsync(out, ob.R, (size_t)d.n3 * r * sizeof(double), dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    if (!dev_ptrs || h->world > 1) return check_abort(h);     // synchronises
     return XM_OK;
 }
 extern "C" int xm_qy(xm_handle* h, int r, double alpha, const double* X, double* out) { return qy_common(h, r, alpha, X, out, false); }
@@ -365,7 +562,8 @@ extern "C" int xm_bench_qy(xm_handle* h, int r, int iters, double* avg_ms) {
     if (rc) return rc;
     if (!avg_ms || iters == 0) return XM_EINVAL;
     Dev d = h->dev;
-    d.qy_alpha = 1.0; d.op_out_R = h->io_Rout;
+    d.qy_alpha = 1.0;
+    (void)bind_out(h, d, h->io_Rout, h->io_sout);
     cudaEvent_t e0, e1;
     XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
     // iters > 0: `iters` products inside ONE launch (steady state, ring prefetch across products, like the solver);
@@ -381,7 +579,7 @@ extern "C" int xm_bench_qy(xm_handle* h, int r, int iters, double* avg_ms) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     h->launches += 2;
     *avg_ms = (double)ms / iters;
-    return XM_OK;
+    return check_abort(h);
 }
 
 // measurement hook: average device time (us) of one grid barrier of the persistent kernel (|iters| barriers, one launch)
@@ -394,8 +592,9 @@ extern "C" int xm_bench_barrier(xm_handle* h, int r, int iters, double* avg_us) 
     d.op_repeat = iters;
     cudaEvent_t e0, e1;
     XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
+    (void)bind_out(h, d, h->io_Rout, h->io_sout);
     XM_CUDA(h, launch_ops(h, d, 5, p, h->stream));
-    XM_CUDA(h, cudaMemsetAsync(h->d_bar, 0, 256, h->stream));
+    if (h->world == 1) XM_CUDA(h, cudaMemsetAsync(h->d_bar, 0, 256, h->stream));
     XM_CUDA(h, cudaEventRecord(e0, h->stream));
     XM_CUDA(h, launch_ops(h, d, 5, p, h->stream));
     XM_CUDA(h, cudaEventRecord(e1, h->stream));
@@ -452,13 +651,16 @@ static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, do
     if (!R0 || !s0 || !gradtol_inout || !R_out || !s_out || (ls_step != 0.0 && !v)) { h->err = "null argument"; return XM_EINVAL; }
     Dev d = h->dev;
     const size_t bR = (size_t)d.n3 * r * sizeof(double), bS = (size_t)d.N * sizeof(double);
+    OutBind ob;
     if (dev_ptrs) {
-        d.R0 = R0; d.s0 = s0; d.vdir = v; d.R_out = R_out; d.s_out = s_out;
+        d.R0 = R0; d.s0 = s0; d.vdir = v;
+        ob = bind_out(h, d, R_out, s_out);
     } else {
         XM_CUDA(h, cudaMemcpyAsync(h->io_R0, R0, bR, cudaMemcpyHostToDevice, h->stream));
         XM_CUDA(h, cudaMemcpyAsync(h->io_s0, s0, bS, cudaMemcpyHostToDevice, h->stream));
         if (ls_step != 0.0) XM_CUDA(h, cudaMemcpyAsync(h->io_v, v, 3 * bS, cudaMemcpyHostToDevice, h->stream));
-        d.R0 = h->io_R0; d.s0 = h->io_s0; d.vdir = h->io_v; d.R_out = h->io_Rout; d.s_out = h->io_sout;
+        d.R0 = h->io_R0; d.s0 = h->io_s0; d.vdir = h->io_v;
+        ob = bind_out(h, d, h->io_Rout, h->io_sout);
     }
     d.lam = lam; d.gradtol = *gradtol_inout; d.ls_step = ls_step; d.max_time = max_time;
     cudaEvent_t e0, e1;
@@ -467,9 +669,10 @@ static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, do
     XM_CUDA(h, launch_solve(h, d, p, h->stream));
     XM_CUDA(h, cudaEventRecord(e1, h->stream));
     h->launches++;
-    if (!dev_ptrs) {
-        XM_CUDA(h, cudaMemcpyAsync(R_out, h->io_Rout, bR, cudaMemcpyDeviceToHost, h->stream));
-        XM_CUDA(h, cudaMemcpyAsync(s_out, h->io_sout, bS, cudaMemcpyDeviceToHost, h->stream));
+    if (!dev_ptrs || ob.R != R_out) {
+        const cudaMemcpyKind kout = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        XM_CUDA(h, cudaMemcpyAsync(R_out, ob.R, bR, kout, h->stream));
+        XM_CUDA(h, cudaMemcpyAsync(s_out, ob.s, bS, kout, h->stream));
     }
     XM_CUDA(h, cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, h->stream));
     XM_CUDA(h, cudaMemcpyAsync(h->h_log, h->d_log, sizeof(LogRec) * kLogCap, cudaMemcpyDeviceToHost, h->stream));
@@ -479,7 +682,7 @@ static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, do
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (rc) return rc;
     const DevStats& S = *h->h_stats;
-    if (S.aborted) { h->err = "solver kernel aborted"; return XM_ESYNC; }
+    if (S.aborted) { h->err = "solver kernel aborted"; if (h->world > 1) h->comm_broken = true; return XM_ESYNC; }
     *gradtol_inout = S.gradtol_out;
     if (primal_out) *primal_out = S.primal;
     if (stats) {
@@ -520,11 +723,11 @@ static int op_common(xm_handle* h, int r, int opcode, const double* R, const dou
     if (P) XM_CUDA(h, cudaMemcpyAsync(h->io_P, P, bR, cudaMemcpyHostToDevice, h->stream));
     if (ps) XM_CUDA(h, cudaMemcpyAsync(h->io_ps, ps, bS, cudaMemcpyHostToDevice, h->stream));
     d.R0 = h->io_R0; d.s0 = h->io_s0; d.op_in_P = h->io_P; d.op_in_ps = h->io_ps; d.op_lr = lr; d.lam = lam;
-    d.op_out_R = h->io_Rout; d.op_out_s = h->io_sout;
+    const OutBind ob = bind_out(h, d, h->io_Rout, h->io_sout);
     XM_CUDA(h, launch_ops(h, d, opcode, p, h->stream));
     h->launches++;
-    if (outR) XM_CUDA(h, cudaMemcpyAsync(outR, h->io_Rout, bR, cudaMemcpyDeviceToHost, h->stream));
-    if (outS) XM_CUDA(h, cudaMemcpyAsync(outS, h->io_sout, bS, cudaMemcpyDeviceToHost, h->stream));
+    if (outR) XM_CUDA(h, cudaMemcpyAsync(outR, ob.R, bR, cudaMemcpyDeviceToHost, h->stream));
+    if (outS) XM_CUDA(h, cudaMemcpyAsync(outS, ob.s, bS, cudaMemcpyDeviceToHost, h->stream));
     if (out_scalar) XM_CUDA(h, cudaMemcpyAsync(out_scalar, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     return check_abort(h);
 }

@@ -69,6 +69,7 @@ extern "C" int xm_certify(xm_handle* h, int r, const double* R, const double* s,
                           double* v_out, double* min_eig_out, double* dual_out, double* gap_out, int* certified_out) {
     if (!h || !R || !s) return XM_EINVAL;
     if (h->is_bsr || !h->Qp) { h->err = "xm_certify needs a dense Q"; return XM_EUNSUPPORTED; }
+    if (h->world > 1) { h->err = "xm_certify is single-GPU only (this rank holds a row slab of Q)"; return XM_EUNSUPPORTED; }
     if (r < 3 || r > XM_MAX_RANK) return XM_EINVAL;
     XM_CUDA(h, cudaSetDevice(h->device));
     const int N = h->N, n3 = h->n3;

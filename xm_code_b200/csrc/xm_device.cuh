@@ -22,7 +22,8 @@ constexpr int kMaxRank = 20;
 constexpr int kLogCap = 1002;
 constexpr int kPartialBufs = 4;
 constexpr int kKC = 192;            // TMA ring: columns per chunk (box inner dimension, <= 256); see profiles/r01_sweep_ring_*.txt
-constexpr int kPartialStride = 1;   // doubles per slot; G slots for the CTA sums + 1 for CTA 0's flag, x kPartialBufs rotating buffers
+constexpr int kPartialStride = 1;   // doubles per slot; GT slots for the CTA sums + 1 for global CTA 0's flag, x kPartialBufs rotating buffers
+constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node that can share a solve (camera partition, peer-mapped exchange)
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
 enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, kNumVecR };
@@ -48,6 +49,20 @@ struct Dev {
     double lam;
     // launch geometry
     int G, NW, KS, CB, W, cpw, NSW;
+    // multi-GPU camera partition.  The solve runs on world * G CTAs: this rank's CTAs are the global CTAs
+    // [g0, g0 + G) of GT and own the cameras (hence the rows of Q) [cam0, cam1).  Only three things cross GPUs, all by
+    // peer-mapped stores over NVLink issued from inside the persistent kernel: the Q.Y operand rows a CTA owns (into every
+    // rank's Xt), one double per CTA per reduction (into every rank's slot array) and the barrier arrivals.  world == 1:
+    // every *_peer[0] is the local buffer and all scopes stay .gpu.
+    int rank, world, GT, g0, cam0, row0;       // row0 = 3 * cam0: first row of Q held by this rank (dense slab / BSR rows)
+    double* Xt_peer[kMaxWorld];
+    double* partials_peer[kMaxWorld];
+    unsigned long long* bar_peer[kMaxWorld];
+    int* abort_peer[kMaxWorld];
+    double* outR_peer[kMaxWorld];              // results in the wire layout (3N x r col-major / length N): every CTA stores its
+    double* outS_peer[kMaxWorld];              // own cameras into every rank's copy
+    unsigned long long* epoch_store;           // local: barrier epoch carried from launch to launch (the counters are never reset
+                                               // while a communicator is live: a peer may already be arriving for the next launch)
     // dense Q.Y through a shared-memory ring fed by 2-D tensor-map TMA (use_tma) or by direct streaming loads
     int use_tma, KC, ST, nbmax, nchunks, stage_doubles;
     int l2_prefetch;           // Q chunks (beyond the ring) prefetched into L2 at the end of a Q.Y phase
@@ -62,9 +77,9 @@ struct Dev {
     double *S6;                // N*6 : sym(Y_i EG_i^T), order 00 01 02 11 12 22
     int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
     int profile;               // fine-grained phase timers on (costs a few percent)
-    double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)
-    double *partials;          // kPartialBufs * G * kPartialStride
-    unsigned* bar;             // grid barrier counter (zeroed before each launch)
+    double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
+    double *partials;          // kPartialBufs * (GT + 1) * kPartialStride             [== partials_peer[rank]]
+    unsigned long long* bar;   // grid barrier counter, monotone                       [== bar_peer[rank]]
     int* abort_flag;
     // trust-region call parameters
     double gradtol, ls_step, max_time;
@@ -72,11 +87,10 @@ struct Dev {
     int replicate_stale_sr, max_outer, max_inner;
     // I/O in the reference wire layout (3N x r column-major; s length N)
     const double* R0; const double* s0;
-    double* R_out; double* s_out;
     DevStats* stats; LogRec* log;
     // standalone ops
     double qy_alpha; const double* op_in_P; const double* op_in_ps; double op_lr;
-    double* op_out_R; double* op_out_s; double* op_out_scalar;
+    double* op_out_scalar;
 };
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -93,9 +107,14 @@ __device__ __forceinline__ double2 ldg_stream_v2(const double* p) {
     return v;
 }
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -163,8 +182,9 @@ struct Ctx {
     const Dev& d;
     int tid, lane, warp, W, cpw, sw, j, slot, NSW;
     bool act;                   // lane holds a real column (j < r)
+    int gc;                     // global CTA index in [0, GT): rank * G + blockIdx.x
     int cam_lo, cam_hi;         // cameras owned by this CTA
-    unsigned epoch;             // grid barrier epoch (thread 0)
+    unsigned long long epoch, epoch_begin;   // barrier epoch (monotone across launches)
     int pbuf;                   // rotating partial buffer
     bool aborted;
     unsigned long long t_qy, t_sync;   // accumulated by CTA 0 thread 0
@@ -191,21 +211,33 @@ struct Ctx {
         W = d.W; cpw = d.cpw; sw = lane / W; j = lane % W; NSW = d.NSW;
         slot = warp * cpw + sw;
         act = j < d.r;
-        cam_lo = (int)(((long long)blockIdx.x * d.N) / d.G);
-        cam_hi = (int)(((long long)(blockIdx.x + 1) * d.N) / d.G);
-        epoch = 0; pbuf = 0; aborted = false; pend_v = 0.0; pend_f = 0.0; t_qy = 0; t_sync = 0; dbg0 = dbg1 = dbg2 = dbg3 = 0; trace_n = 0; trace_on = false;
+        gc = d.g0 + (int)blockIdx.x;
+        cam_lo = (int)(((long long)gc * d.N) / d.GT);
+        cam_hi = (int)(((long long)(gc + 1) * d.N) / d.GT);
+        // barrier epoch continues where the previous launch on this communicator stopped (identical on every rank: all
+        // ranks run the same number of barriers per launch); the host zeroes it together with the counter when world == 1
+        epoch = __ldcg(d.epoch_store); epoch_begin = epoch;
+        pbuf = (int)(epoch % (unsigned long long)kPartialBufs);
+        aborted = false; pend_v = 0.0; pend_f = 0.0; t_qy = 0; t_sync = 0; dbg0 = dbg1 = dbg2 = dbg3 = 0; trace_n = 0; trace_on = false;
         red = red_; bsum = bsum_; bcast = bcast_;
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
         ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
     }
+    // end of a launch: remember the epoch for the next one (every CTA has long read epoch_store by now: it sits behind at
+    // least one barrier whenever the value changes)
+    __device__ __forceinline__ void save_epoch() {
+        if (blockIdx.x == 0 && tid == 0 && epoch != epoch_begin) *d.epoch_store = epoch;
+    }
 
-    // ---- grid-wide barrier fused with a deterministic all-reduce (all CTAs co-resident: cooperative launch).
-    // Arrival: release fence, this CTA's partial sum into its slot, one RED.add on a monotone counter.  Thread 0 spins on
-    // the counter (one hot line, 148 pollers); once it is complete warp 0 reads all slots (one more L2 round trip) and adds
-    // them in slot order: identical bits in every CTA, run to run.  (Measured alternatives — all-to-all slot polling with
-    // tagged values, with or without the counter — were slower: the polling traffic on ~20 hot lines outweighs the saved
-    // round trip; profiles/r01_barrier_variants.txt.)
+    // ---- barrier over all GT = world * G CTAs fused with a deterministic all-reduce (the CTAs of a rank are co-resident:
+    // cooperative launch; the ranks' kernels run concurrently).
+    // Arrival: this CTA's partial sum into its slot of EVERY rank's slot array, release fence, one RED.add on EVERY rank's
+    // monotone counter (peer-mapped memory: the stores and the atomics travel over NVLink; world == 1: one local slot, one
+    // local RED, .gpu scope).  Thread 0 spins on the LOCAL counter; once it shows GT arrivals warp 0 reads all GT slots from
+    // local memory and adds them in slot order: identical bits in every CTA of every rank, run to run.  (Measured single-GPU
+    // alternatives — all-to-all slot polling with tagged values, with or without the counter — were slower: the polling
+    // traffic on ~20 hot lines outweighs the saved round trip; profiles/r01_barrier_variants.txt.)
     double pend_v, pend_f;
     __device__ __forceinline__ void publish(double v, double flag = 0.0) {
         v = warpsum(v);
@@ -217,45 +249,76 @@ struct Ctx {
             pend_v = t; pend_f = flag;
         }
     }
+    __device__ __forceinline__ void raise_abort() {
+        for (int w = 0; w < d.world; ++w) *(volatile int*)d.abort_peer[w] = 1;
+    }
     __device__ __forceinline__ bool grid_sync() {
         __syncthreads();
-        epoch += 1;                                           // uniform in every thread of every CTA
+        epoch += 1;                                           // uniform in every thread of every CTA of every rank
         if (warp == 0) {
             unsigned long long t0 = 0;
             if (tid == 0) t0 = gtimer();
-            double* slots = d.partials + (size_t)pbuf * (d.G + 1);
-            const unsigned target = epoch * (unsigned)d.G;
+            const int GT = d.GT;
+            const size_t soff = (size_t)pbuf * (GT + 1);
+            const double* slots = d.partials + soff;
+            const unsigned long long target = epoch * (unsigned long long)GT;
             int ok = 1;
             if (tid == 0) {
-                slots[blockIdx.x] = pend_v;
-                if (blockIdx.x == 0) slots[d.G] = pend_f;                   // CTA 0's flag rides in the extra slot G
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");            // release everything this CTA wrote
-                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(d.bar) : "memory");
-                pend_v = 0.0; pend_f = 0.0;
                 unsigned spins = 0;
+                if (d.world == 1) {
+                    d.partials[soff + gc] = pend_v;
+                    if (gc == 0) d.partials[soff + GT] = pend_f;                // global CTA 0's flag rides in the extra slot GT
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");            // release everything this CTA wrote
+                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(d.bar) : "memory");
 #pragma unroll 1
-                while (ld_acquire_u32(d.bar) < target) {
-                    if ((++spins & 0x3ffu) == 0) {
-                        if (*(volatile int*)d.abort_flag) { ok = 0; break; }
-                        if (gtimer() - t0 > 4000000000ull) { *(volatile int*)d.abort_flag = 1; ok = 0; break; }
+                    while (ld_acquire_gpu_u64(d.bar) < target) {
+                        if ((++spins & 0x3ffu) == 0) {
+                            if (*(volatile int*)d.abort_flag) { ok = 0; break; }
+                            if (gtimer() - t0 > 4000000000ull) { *(volatile int*)d.abort_flag = 1; ok = 0; break; }
+                        }
                     }
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");            // acquire
+                } else {
+#pragma unroll 1
+                    for (int w = 0; w < d.world; ++w) {
+                        d.partials_peer[w][soff + gc] = pend_v;
+                        if (gc == 0) d.partials_peer[w][soff + GT] = pend_f;
+                    }
+                    // system-scope release: the operand rows / results the CTA's threads stored into peer memory before the
+                    // __syncthreads above, and the slots, are visible on every GPU before the arrivals below
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+#pragma unroll 1
+                    for (int w = 0; w < d.world; ++w)
+                        asm volatile("red.relaxed.sys.global.add.u64 [%0], 1;" ::"l"(d.bar_peer[w]) : "memory");
+#pragma unroll 1
+                    while (ld_acquire_sys_u64(d.bar) < target) {
+                        if ((++spins & 0x3ffu) == 0) {
+                            if (*(volatile int*)d.abort_flag) { ok = 0; break; }
+                            // generous: the ranks' hosts launch independently (a peer may reach its launch seconds later)
+                            if (gtimer() - t0 > 30000000000ull) { raise_abort(); ok = 0; break; }
+                        }
+                    }
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
                 }
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");            // acquire
+                pend_v = 0.0; pend_f = 0.0;
             }
             __syncwarp();
-            constexpr int MAXS = 5;                                          // G + 1 <= 160 slots -> at most 5 per lane
-            double w[MAXS];
-#pragma unroll
-            for (int q = 0; q < MAXS; ++q) {                                 // independent loads: one L2 round trip
-                const int sl = lane + 32 * q;
-                w[q] = (sl <= d.G) ? __ldcg(slots + sl) : 0.0;
-            }
+            constexpr int MAXS = 5;                                          // slots per lane and pass; one pass when GT + 1 <= 160
             double acc = 0.0, f0 = 0.0;
+#pragma unroll 1
+            for (int base = 0; base <= GT; base += 32 * MAXS) {
+                double w[MAXS];
 #pragma unroll
-            for (int q = 0; q < MAXS; ++q) {                                 // fixed slot order per lane
-                const int sl = lane + 32 * q;
-                if (sl < d.G) acc += w[q];
-                if (sl == d.G) f0 = w[q];
+                for (int q = 0; q < MAXS; ++q) {                             // independent loads: one L2 round trip per pass
+                    const int sl = base + lane + 32 * q;
+                    w[q] = (sl <= GT) ? __ldcg(slots + sl) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < MAXS; ++q) {                             // fixed slot order per lane
+                    const int sl = base + lane + 32 * q;
+                    if (sl < GT) acc += w[q];
+                    if (sl == GT) f0 = w[q];
+                }
             }
             acc = warpsum(acc);
             f0 = warpsum(f0);                                                // exactly one lane holds the flag, the rest add 0
@@ -288,11 +351,34 @@ __device__ __forceinline__ void st3(double* A, int i, int r, int j, bool act, co
         p[0] = x[0]; p[r] = x[1]; p[2 * r] = x[2];
     }
 }
-// operand store (j-major, padded ld)
-__device__ __forceinline__ void st_operand(double* Xt, int ldq, int i, int j, bool act, const double (&x)[3]) {
+// operand store (j-major, padded ld): the local copy, then every peer's copy (multi-GPU: this IS the all-gather of the
+// Q.Y operand — each CTA pushes the rows of its own cameras over NVLink; the next barrier publishes them)
+template <class C>
+__device__ __forceinline__ void st_operand(const C& c, int i, bool act, const double (&x)[3]) {
     if (act) {
-        double* p = Xt + (size_t)j * ldq + 3 * i;
+        const size_t off = (size_t)c.j * c.d.ldq + 3 * i;
+        double* p = c.d.Xt + off;
         p[0] = x[0]; p[1] = x[1]; p[2] = x[2];
+        if (c.d.world > 1) {
+#pragma unroll 1
+            for (int w = 0; w < c.d.world; ++w) {
+                if (w == c.d.rank) continue;
+                double* q = c.d.Xt_peer[w] + off;
+                q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
+            }
+        }
+    }
+}
+// result store in the wire layout (3N x r column-major) into every rank's output copy
+template <class C>
+__device__ __forceinline__ void st_out3(const C& c, int i, bool act, const double (&x)[3]) {
+    if (act) {
+        const size_t off = (size_t)c.j * c.d.n3 + 3 * i;
+#pragma unroll 1
+        for (int w = 0; w < c.d.world; ++w) {
+            double* q = c.d.outR_peer[w] + off;
+            q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
+        }
     }
 }
 // symmetric 3x3 (00 01 02 11 12 22) times vector
@@ -333,7 +419,7 @@ template <int RP>
 __device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, int kend, int lane, double (&acc)[3][RP]) {
     const int r = d.r;
     const size_t ldq = (size_t)d.ldq;
-    const double* q0p = d.Q + (size_t)(3 * cam) * ldq;
+    const double* q0p = d.Q + (size_t)(3 * cam - d.row0) * ldq;   // d.Q holds rows [row0, ...) only
     const double* xt = d.Xt;
 #pragma unroll 4
     for (int k = kbeg + 2 * lane; k < kend; k += 64) {
@@ -358,7 +444,7 @@ template <int RP>
 __device__ __forceinline__ void qy_sweep_bsr(const Dev& d, int cam, int part, int nparts, int lane, double (&acc)[3][RP]) {
     const int r = d.r;
     const size_t ldq = (size_t)d.ldq;
-    const int b0 = d.bsr_rowptr[cam], b1 = d.bsr_rowptr[cam + 1];
+    const int b0 = d.bsr_rowptr[cam - d.cam0], b1 = d.bsr_rowptr[cam - d.cam0 + 1];   // local block rows [cam0, cam1)
     const double* xt = d.Xt;
     for (int b = b0 + part * 32 + lane; b < b1; b += 32 * nparts) {
         const int c = d.bsr_col[b];
@@ -460,10 +546,8 @@ __device__ __forceinline__ double qy_batch_epilogue(Ctx<RP, NT>& c, const ObjArg
             }
         }
         if (MODE == MODE_OUT) {
-            if (valid && c.act) {
-                double* o = d.op_out_R + (size_t)c.j * d.n3 + 3 * i;   // column-major 3N x r
-                o[0] = d.qy_alpha * E[0]; o[1] = d.qy_alpha * E[1]; o[2] = d.qy_alpha * E[2];
-            }
+            const double o[3] = {d.qy_alpha * E[0], d.qy_alpha * E[1], d.qy_alpha * E[2]};
+            st_out3(c, i, valid && c.act, o);                                  // column-major 3N x r
         } else if (MODE == MODE_HESS) {
             part = epi_hess<RP, NT>(c, i, E, valid);
         } else {
@@ -562,7 +646,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
                 if (c.lane == 0) {      // ONE op for the whole batch: [3*nb rows x KC] (TMA cost is per op, ~60-100 ns)
                     const CUtensorMap* mq = (nb == d.box_nb[0]) ? mapQ3 : (nb == d.box_nb[1]) ? mapQ3 + 1 : mapQ3 + 2;
                     mbar_expect_tx(&c.fullQ[s], (unsigned)(3 * nb * KC * sizeof(double)));
-                    tma_load_2d(st, mq, ch * KC, 3 * b0, &c.fullQ[s]);
+                    tma_load_2d(st, mq, ch * KC, 3 * b0 - d.row0, &c.fullQ[s]);
                 }
             }
             if (!spec && c.lane == 0) {
@@ -577,10 +661,10 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
                 const int bi = uu / nchunks, ch = uu - bi * nchunks;
                 const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
                 const CUtensorMap* mq = (nb == d.box_nb[0]) ? mapQ3 : (nb == d.box_nb[1]) ? mapQ3 + 1 : mapQ3 + 2;
-                tma_prefetch_l2_2d(mq, ch * KC, 3 * b0);
+                tma_prefetch_l2_2d(mq, ch * KC, 3 * b0 - d.row0);
             }
         }
-        if (!ok && c.lane == 0) *(volatile int*)d.abort_flag = 1;
+        if (!ok && c.lane == 0) c.raise_abort();
     } else {
         // ------------------------------------------------ consumers
         const int cslot = c.warp / KS, ks = c.warp % KS;
@@ -642,7 +726,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
             named_bar_sync(1, NWC * 32);
             if (d.profile && blockIdx.x == 0 && c.tid == 0) c.dbg3 += gtimer() - te0;
         }
-        if (!ok && c.lane == 0) *(volatile int*)d.abort_flag = 1;
+        if (!ok && c.lane == 0) c.raise_abort();
     }
     c.g_use = g0 + (unsigned)uses;
     c.prefetched = npre;

@@ -19,7 +19,8 @@ struct xm_handle {
     char* ws = nullptr; size_t ws_cap = 0; int ws_r = -1, ws_N = -1, ws_G = -1, ws_ldq = -1;
     xm::Dev dev{};                                         // pointer template, filled by carve()
     // small persistent device objects
-    xm::DevStats* d_stats = nullptr; xm::LogRec* d_log = nullptr; unsigned* d_bar = nullptr; int* d_abort = nullptr;
+    xm::DevStats* d_stats = nullptr; xm::LogRec* d_log = nullptr; int* d_abort = nullptr;
+    unsigned long long* d_bar = nullptr;               // 256 B: [0] barrier counter (single GPU), [16] epoch carried across launches
     double* d_scalar = nullptr;
     // I/O staging in the wire layout (device)
     double *io_R0 = nullptr, *io_s0 = nullptr, *io_v = nullptr, *io_Rout = nullptr, *io_sout = nullptr, *io_P = nullptr, *io_ps = nullptr;
@@ -31,6 +32,16 @@ struct xm_handle {
     CUtensorMap mapQ[3]{}, mapX{};
     void* encode_tiled = nullptr;       // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     int smem_optin = 0;                 // max opt-in dynamic shared memory per block
+    // operator rows held by this handle: cameras [cam0, cam1) (all of them unless a communicator is attached)
+    int cam0 = 0, cam1 = 0;
+    // multi-GPU communicator (xm_comm_*): one peer-mapped arena per rank with an identical layout everywhere
+    //   [bar 256][abort 256][partials][Xt: max_r * ldq][outR: n3 * max_r][outS: N]
+    int world = 1, rank = 0, comm_G = 0, comm_N = 0, comm_maxr = 0;
+    bool comm_connected = false, comm_broken = false;
+    char* arena = nullptr; size_t arena_bytes = 0;
+    char* peer_arena[xm::kMaxWorld] = {};
+    bool peer_ipc[xm::kMaxWorld] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
+    size_t off_bar = 0, off_abort = 0, off_partials = 0, off_xt = 0, off_outR = 0, off_outS = 0;
 };
 
 #define XM_CUDA(h, call)                                                                           \

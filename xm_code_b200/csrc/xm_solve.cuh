@@ -30,20 +30,21 @@ __device__ __forceinline__ void phase_load_point(Ctx<RP, NT>& c, const double* R
         if (valid && c.j == 0) c.S(c.iS)[i] = (i == 0) ? 1.0 : s0[i];
     }
 }
-// ---- exit: camera-block state -> wire layout
+// ---- exit: camera-block state -> wire layout (every rank's output copy gets this CTA's cameras)
 template <int RP, int NT>
-__device__ __forceinline__ void phase_store_point(Ctx<RP, NT>& c, const double* Y, const double* s, double* R_out, double* s_out) {
+__device__ __forceinline__ void phase_store_point(Ctx<RP, NT>& c, const double* Y, const double* s) {
     const Dev& d = c.d;
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
         double y[3];
         ld3(Y, i, d.r, c.j, act, y);
-        if (act) {
-            double* p = R_out + (size_t)c.j * d.n3 + 3 * i;
-            p[0] = y[0]; p[1] = y[1]; p[2] = y[2];
+        st_out3(c, i, act, y);
+        if (valid && c.j == 0) {
+            const double si = s[i];
+#pragma unroll 1
+            for (int w = 0; w < d.world; ++w) d.outS_peer[w][i] = si;
         }
-        if (valid && c.j == 0) s_out[i] = s[i];
     }
 }
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void phase_operand_sR(Ctx<RP, NT>& c, const double* Y
         ld3(Y, i, d.r, c.j, act, y);
         const double si = valid ? s[i] : 0.0;
         double x[3] = {si * y[0], si * y[1], si * y[2]};
-        st_operand(d.Xt, d.ldq, i, c.j, act, x);
+        st_operand(c, i, act, x);
     }
 }
 
@@ -80,7 +81,7 @@ __device__ __forceinline__ void phase_ls_trial(Ctx<RP, NT>& c, double alpha) {
         st3(c.R(c.iYn), i, d.r, c.j, act, a);
         const double si = valid ? c.S(c.iS)[i] : 0.0;
         double x[3] = {si * a[0], si * a[1], si * a[2]};
-        st_operand(d.Xt, d.ldq, i, c.j, act, x);
+        st_operand(c, i, act, x);
     }
 }
 
@@ -120,7 +121,7 @@ __device__ __forceinline__ double phase_grad(Ctx<RP, NT>& c, bool build_operand)
         if (build_operand) {
             const double psi = -rgs;
             double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
-            st_operand(d.Xt, d.ldq, i, c.j, act, x);
+            st_operand(c, i, act, x);
         }
     }
     return part;
@@ -190,7 +191,7 @@ __device__ __forceinline__ void phase_dir(Ctx<RP, NT>& c, double beta) {
         st3(c.R(V_P), i, r, c.j, act, p);
         if (valid && c.j == 0 && i > 0) c.S(S_PS)[i] = psi;
         double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
-        st_operand(d.Xt, d.ldq, i, c.j, act, x);
+        st_operand(c, i, act, x);
     }
 }
 
@@ -226,7 +227,7 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
         const double sn = (i == 0) ? si : si * exp(lr * vsi / si);   // positiveManifoldRetractionKernal :18-24
         if (valid && c.j == 0) c.S(c.iSn)[i] = sn;
         double x[3] = {sn * a[0], sn * a[1], sn * a[2]};
-        st_operand(d.Xt, d.ldq, i, c.j, act, x);
+        st_operand(c, i, act, x);
     }
     return part;
 }
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
 
     for (k = 0; k < d.max_outer; ++k) {
         double tflag = 0.0;
-        if (lead) tflag = ((double)((gtimer() - t_loop0) / 1000000000ull) > d.max_time) ? 1.0 : 0.0;   // :538-543
+        if (c.gc == 0 && c.tid == 0) tflag = ((double)((gtimer() - t_loop0) / 1000000000ull) > d.max_time) ? 1.0 : 0.0;   // :538-543 (one clock decides for all ranks)
         const double part = phase_grad(c, true);
         c.publish(part, tflag); XM_GSYNC(c);
         double timeflag = 0.0;
@@ -394,7 +395,11 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
 
 xm_finish:
     ring_drain(c);
-    phase_store_point(c, c.R(c.iY), c.S(c.iS), d.R_out, d.s_out);
+    phase_store_point(c, c.R(c.iY), c.S(c.iS));
+    // multi-GPU: the result rows were pushed into every rank's output copy; nobody's host may read its copy (or launch the
+    // next solve, which rewrites the peers' operand) before all of them have landed
+    if (d.world > 1) { if (!c.grid_sync()) goto xm_abort; }
+    c.save_epoch();
     if (lead) {
         DevStats& S = *d.stats;
         S.exit_code = exit_code; S.outer_iters = k; S.tcg_iters = totalite; S.qy_products = nqy;
@@ -417,14 +422,7 @@ xm_abort:
 //         3 = Riemannian Hessian-vector at (R0,s0) along (P,ps)     -> op_out_R = HpR, op_out_s = Hps
 //         4 = retraction of (R0,s0) along (P,ps) with step op_lr    -> op_out_R = Rn, op_out_s = sn
 template <int RP, int NT, int PATH>
-__global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
-                                                       const __grid_constant__ CUtensorMap mapX, const int opcode) {
-    __shared__ double red[(NT / 32) * 3 * RP];
-    __shared__ double bsum[NT / 32];
-    __shared__ double bcast[4];
-    extern __shared__ unsigned char dyn_smem[];
-    Ctx<RP, NT> c(d, red, bsum, bcast);
-    ring_init(c, dyn_smem);
+__device__ __forceinline__ bool ops_body(Ctx<RP, NT>& c, const Dev& d, const QMaps& mapsQ, const CUtensorMap& mapX, const int opcode) {
     if (opcode == 0) {
         ObjArgs oa{nullptr, nullptr, nullptr};
         // op_repeat > 1 (xm_bench_qy): back-to-back products inside one launch, ring prefetch across them as in the solver
@@ -435,12 +433,12 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ D
             else __syncthreads();
         }
         if (blockIdx.x == 0 && c.tid == 0) { d.stats->dbg[0] = c.dbg0; d.stats->dbg[1] = c.dbg1; d.stats->dbg[2] = c.dbg2; d.stats->dbg[3] = c.dbg3; d.stats->qy_ns = c.t_qy; d.stats->sync_ns = c.t_sync; }
-        return;
+        return true;
     }
     if (opcode == 5) {                 // grid-barrier micro-benchmark: |op_repeat| barriers back to back
         const int nrep = d.op_repeat < 0 ? -d.op_repeat : d.op_repeat;
         for (int rep = 0; rep < nrep; ++rep) { XM_GSYNC(c); }
-        return;
+        return true;
     }
     phase_load_point(c, d.R0, d.s0);
     if (opcode == 4) {
@@ -455,8 +453,8 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ D
             if (valid && c.j == 0) c.S(S_VS)[i] = (i == 0) ? 0.0 : d.op_in_ps[i];
         }
         (void)phase_model_retract(c, c.R(V_V), c.S(S_VS), d.op_lr, false);
-        phase_store_point(c, c.R(c.iYn), c.S(c.iSn), d.op_out_R, d.op_out_s);
-        return;
+        phase_store_point(c, c.R(c.iYn), c.S(c.iSn));
+        return true;
     }
     phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
     XM_GSYNC(c);
@@ -465,7 +463,7 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ D
         double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX, opcode == 3);
         c.publish(part); XM_GSYNC(c);
         const double f = c.collect();
-        if (opcode == 1) { if (blockIdx.x == 0 && c.tid == 0) d.op_out_scalar[0] = f; return; }
+        if (opcode == 1) { if (blockIdx.x == 0 && c.tid == 0) d.op_out_scalar[0] = f; return true; }
     }
     {
         double part = phase_grad(c, false);
@@ -473,8 +471,8 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ D
         const double rd = c.collect();
         if (opcode == 2) {
             if (blockIdx.x == 0 && c.tid == 0) d.op_out_scalar[0] = sqrt(rd);
-            phase_store_point(c, c.R(V_RG), c.S(S_RGS), d.op_out_R, d.op_out_s);
-            return;
+            phase_store_point(c, c.R(V_RG), c.S(S_RGS));
+            return true;
         }
     }
     // opcode 3: overwrite P / ps with the caller's direction, build the operand, one Hessian-vector product
@@ -492,18 +490,33 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ D
         const double psi = (valid && i > 0) ? d.op_in_ps[i] : 0.0;
         if (valid && c.j == 0) c.S(S_PS)[i] = psi;
         double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
-        st_operand(d.Xt, d.ldq, i, c.j, act, x);
+        st_operand(c, i, act, x);
     }
     XM_GSYNC(c);
     {
         ObjArgs oa{nullptr, nullptr, nullptr};
         (void)qy_phase<RP, NT, MODE_HESS, PATH>(c, oa, mapsQ.m, &mapX, false);
-        phase_store_point(c, c.R(V_HP), c.S(S_HPS), d.op_out_R, d.op_out_s);
+        phase_store_point(c, c.R(V_HP), c.S(S_HPS));
     }
-    return;
+    return true;
 xm_abort:
-    ring_drain(c);
-    return;
+    return false;
+}
+
+template <int RP, int NT, int PATH>
+__global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
+                                                       const __grid_constant__ CUtensorMap mapX, const int opcode) {
+    __shared__ double red[(NT / 32) * 3 * RP];
+    __shared__ double bsum[NT / 32];
+    __shared__ double bcast[4];
+    extern __shared__ unsigned char dyn_smem[];
+    Ctx<RP, NT> c(d, red, bsum, bcast);
+    ring_init(c, dyn_smem);
+    bool ok = ops_body<RP, NT, PATH>(c, d, mapsQ, mapX, opcode);
+    // multi-GPU: results were pushed to every rank and the peers' operand copies may still be in use — leave together
+    if (ok && d.world > 1) ok = c.grid_sync();
+    if (ok) c.save_epoch();
+    else ring_drain(c);
 }
 
 }  // namespace xm
