@@ -11,6 +11,7 @@
  *   xm_op_*             <- the lambdas objc/grad/projection/ehess+ehess2rhess/retraction        XM/include/XM/trustregion.h:162-351
  *   xm_certify          <- checkeig(C,sR,lam,v,primal)                                          XM/include/XM/checkeig.h:42-368
  *   xm_escape_scale     <- DecentDirectionKernal                                                XM/src/XM_main.cu:8-16
+ *   xm_recover          <- recover_XM(Q,R,s,Abar,lam)                                           utils/recoversolution.py:4-86
  *
  * Matrix arguments use the reference's wire layouts: R is 3N x r COLUMN-MAJOR with
  * rows 3i..3i+2 = camera i; s is length N with s[0] == 1 (the reference's s_ex); v is length 3N.
@@ -160,6 +161,15 @@ int  xm_op_retract(xm_handle* h, int r, const double* R, const double* s, const 
  * eigenvalue of the dual slack.  certified_out: 1/0. */
 int  xm_certify(xm_handle* h, int r, const double* R, const double* s, double lam, double primal,
                 double* v_out, double* min_eig_out, double* dual_out, double* gap_out, int* certified_out);
+/* Solution recovery (recover_XM): rank-r -> 3 (top-3 eigenvectors of (sR)^T(sR)), per-camera scale ||block||_F / sqrt(3),
+ * anchoring by camera 0, projection of every 3x3 block to O(3) (polar factor U V^T), global sign by majority of det, and
+ * [t p] = Abar (sR)^T.  R: 3N x r col-major; s: N.  Abar: abar_rows x 3N COLUMN-MAJOR (abar_rows = N + M - 1, the
+ * reference's Abar.bin) or NULL.  Outputs (host): R_out 3 x 3N col-major (camera i = columns 3i..3i+2), s_out N,
+ * y_out 3 x (abar_rows + 1) col-major = [t | p] with the zero first column (required iff Abar), eig_out r eigenvalues of
+ * (sR)^T(sR) descending (zeros when r == 3; may be NULL), negative_out = cameras whose block had det < 0 (may be NULL).
+ * The reference's Q and lam arguments only feed a printed diagnostic and are not needed.  Works on any handle (no Q). */
+int  xm_recover(xm_handle* h, int n_cameras, int r, const double* R, const double* s, const double* Abar, int64_t abar_rows,
+                double* R_out, double* s_out, double* y_out, double* eig_out, int* negative_out);
 /* v[3i..3i+2] /= s[i]  (DecentDirectionKernal) — host-side helper, trivial. */
 int  xm_escape_scale(int n_cameras, double* v, const double* s);
 

@@ -19,6 +19,8 @@ Reference files restated here (all paths relative to /root/reference):
   XM/include/XM/trustregion.h:18-48    scale kernels (retraction exp, lambda terms with the i+1 offsets)
   XM/src/XM_main.cu:180-310            rank staircase (solve), :312-401 solve_rank3, :35-178 solve_rebuttle
   XM/include/XM/checkeig.h:42-368      optimality certificate (multipliers, dual slack, min eig, gap)
+  utils/recoversolution.py:4-86        recover_XM (rank-r -> 3, per-camera scale, anchoring, O(3) projection, t/p);
+                                        pinned by tests/golden/recover_ref.npz (outputs of the reference function itself)
 
 Layout used here: a point is ``Y`` of shape (N, 3, r) (camera i's 3 x r block, rows orthonormal) and
 ``s`` of shape (N,) with s[0] == 1 pinned (the reference's ``s_ex``; its ``s`` is the view s_ex[1:]).
@@ -441,6 +443,42 @@ def solve(Q, max_rank, tol, lam, max_time=1000.0, rank3_only=False, Y_init=None,
             status = 2
         o += 1
     return dict(R=from_blocks(Y0), s=np.asarray(s0), rank=o - 1, status=status, trace=trace)
+
+
+# --------------------------------------------------------------------------- solution recovery (utils/recoversolution.py:4-86)
+def recover(R, s, Abar=None):
+    """recover_XM restated.  R: 3N x r, s: (N,), Abar: (N+M-1) x 3N or None.
+    Returns dict(R (3 x 3N), s (N,), t (3 x N), p (3 x M), eigvals (descending, of (sR)(sR)^T; None when r == 3),
+    negative = number of cameras whose projected block had det < 0 before the global sign decision)."""
+    R = np.asarray(R, dtype=np.float64); s = np.asarray(s, dtype=np.float64).reshape(-1)
+    N = s.shape[0]
+    sR = R * np.repeat(s, 3)[:, None]                                   # :7-9
+    eigvals = None
+    if R.shape[1] > 3:                                                   # :11-23
+        w, V = np.linalg.eigh(sR @ sR.T)
+        idx = np.argsort(w)[::-1]
+        w, V = w[idx], V[:, idx]
+        sR_real = (V[:, :3] * np.sqrt(w[:3])).T
+        eigvals = w
+    else:                                                                # :32-37
+        sR_real = sR.T.copy()
+    blocks = sR_real.reshape(3, N, 3).transpose(1, 0, 2)                 # blocks[i] = sR_real[:, 3i:3i+3]
+    s_real = np.linalg.norm(blocks, axis=(1, 2)) / np.sqrt(3.0)          # :42-44
+    Rb = blocks / s_real[:, None, None]
+    Rb = Rb[0].T @ Rb                                                    # anchoring :47-48
+    U, _, Vt = np.linalg.svd(Rb)
+    UV = U @ Vt
+    negative = int(np.sum(np.linalg.det(UV) < 0))                        # :50-55
+    if negative > N / 2:                                                 # :62-63
+        UV = -UV                                                         # polar(-M) = -polar(M)
+    Rb = UV                                                              # :65-73 (both branches assign U Vt)
+    R_real = Rb.transpose(1, 0, 2).reshape(3, 3 * N)
+    out = dict(R=R_real, s=s_real, eigvals=eigvals, negative=negative, t=None, p=None)
+    if Abar is not None:
+        sR_out = (Rb * s_real[:, None, None]).transpose(1, 0, 2).reshape(3, 3 * N)
+        y = np.hstack([np.zeros((3, 1)), (np.asarray(Abar) @ sR_out.T).T])   # :76-82
+        out["t"] = y[:, :N]; out["p"] = y[:, N:]
+    return out
 
 
 # --------------------------------------------------------------------------- .bin wire format (utils/io.py:17-58)

@@ -5,6 +5,8 @@
   simple2_obs.npz          SIMPLE2 observations after the preprocessing of 2_test_creatematrix.py:29-144
                            (edges 1-based like the reference, weights, camera-frame points) + ground-truth rotations
   simple2_Q_ref.npz        Q (279 x 279) produced by the reference's own utils/creatematrix.create_matrix on them
+  recover_ref.npz          inputs/outputs of the reference's own utils/recoversolution.recover_XM (24 cameras, Q and Abar
+                           from the reference's create_matrix): rank-3, rank-5 and mirrored cases
 """
 import io
 import os
@@ -76,5 +78,54 @@ def main():
     shutil.rmtree(tmp)
 
 
+def make_recover_goldens():
+    """recover_ref.npz: inputs and outputs of the reference's OWN utils/recoversolution.recover_XM on a small problem whose
+    Q / Abar come from the reference's OWN create_matrix: (a) a rank-3 point, (b) a rank-5 point (top-3 eigen branch),
+    (c) most cameras reflected (the global sign decision fires), (d) a few cameras reflected."""
+    from utils.creatematrix import create_matrix
+    from utils.recoversolution import recover_XM
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from xm_code_b200 import problems
+    prob = problems.synthetic_sfm(24, n_landmarks=160, obs_per_camera=30, seed=7)
+    N, M = prob["N"], prob["M"]
+    edges = np.stack([prob["cam"] + 1, prob["lm"] + 1], axis=1).astype(int)
+    tmp = tempfile.mkdtemp()
+    with contextlib.redirect_stdout(io.StringIO()):
+        create_matrix(prob["w"], edges, prob["pt"], tmp)
+    Q = load_bin(f"{tmp}/Q.bin"); Abar = load_bin(f"{tmp}/Abar.bin")
+    shutil.rmtree(tmp)
+    rng = np.random.default_rng(5)
+    out = dict(Q=Q, Abar=Abar, N=N, M=M)
+    gt = np.concatenate([prob["R"][i] for i in range(N)], axis=0)      # 3N x 3, camera blocks stacked
+    cases = {}
+    # (a) near-ground-truth rank-3 point in an arbitrary gauge
+    G, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    cases["a"] = (gt @ G + 1e-3 * rng.standard_normal((3 * N, 3)), prob["s"].copy())
+    # (b) rank 5: the same embedded in 5 columns by a random orthonormal frame + small off-subspace noise
+    F, _ = np.linalg.qr(rng.standard_normal((5, 5)))
+    R5 = np.concatenate([gt, np.zeros((3 * N, 2))], axis=1) @ F + 2e-3 * rng.standard_normal((3 * N, 5))
+    cases["b"] = (R5, prob["s"] * rng.uniform(0.9, 1.1, N))
+    # (c) most cameras (not the anchor) reflected -> "negative > N/2" global sign flip; (d) a minority reflected
+    D = np.diag([1.0, 1.0, -1.0])
+    Rc = gt.copy(); Rd = gt.copy()
+    for i in range(1, N):
+        if i % 3 != 0:
+            Rc[3 * i:3 * i + 3] = Rc[3 * i:3 * i + 3] @ D
+        if i % 5 == 1:
+            Rd[3 * i:3 * i + 3] = Rd[3 * i:3 * i + 3] @ D
+    cases["c"] = (Rc + 1e-3 * rng.standard_normal((3 * N, 3)), prob["s"].copy())
+    cases["d"] = (Rd + 1e-3 * rng.standard_normal((3 * N, 3)), prob["s"].copy())
+    for k, (R, s) in cases.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            R_real, s_real, p_est, t_est = recover_XM(Q, R, s[:, None], Abar, 0.0)
+        out.update({f"{k}_R_in": R, f"{k}_s_in": s, f"{k}_R": R_real, f"{k}_s": s_real, f"{k}_p": p_est, f"{k}_t": t_est})
+    np.savez_compressed(f"{HERE}/recover_ref.npz", **out)
+    print("recover goldens: N", N, "M", M, "Abar", Abar.shape)
+
+
 if __name__ == "__main__":
-    main()
+    if "--recover" in sys.argv:          # only the recover_XM fixture
+        make_recover_goldens()
+    else:
+        main()
+        make_recover_goldens()

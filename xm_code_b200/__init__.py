@@ -3,8 +3,8 @@
 Host-side Python mirror of the reference surface for this path only:
 
   * ``capi``      ctypes binding of the C-ABI (include/xm_b200.h, libxm_b200.so) — what tests and bench.py call
-  * ``solver``    ``solve`` / ``solve_rank3`` / ``solve_rebuttle`` with the reference's path-based semantics
-                  (XM/src/XM_main.cu:35-401), driving the C-ABI
+  * ``dist``      torch.distributed plumbing for one solve partitioned by camera over the GPUs of a node
+  * ``recover``   ``recover_XM`` with the reference's signature (utils/recoversolution.py:4-86) on the GPU
   * ``binio``     the ``.bin`` wire format (utils/io.py:17-58)
   * ``problems``  synthetic Q generators for the BASELINE configs (no reference code involved)
 
@@ -13,4 +13,4 @@ same three functions from C++ for the reference's demo scripts.  Nothing in this
 """
 from . import binio  # noqa: F401
 
-__all__ = ["binio", "capi", "solver", "problems"]
+__all__ = ["binio", "capi", "dist", "recover", "problems"]

@@ -43,7 +43,7 @@ EXPORTS = [
     "xm_op_objective", "xm_op_rgrad", "xm_op_rhess", "xm_op_retract", "xm_certify", "xm_escape_scale", "xm_bench_qy",
     "xm_bench_barrier", "xm_debug_trace",
     "xm_partition", "xm_comm_init", "xm_comm_connect", "xm_comm_connect_ptrs", "xm_comm_arena", "xm_comm_info", "xm_comm_reset", "xm_comm_disconnect",
-    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev",
+    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover",
 ]
 XM_IPC_HANDLE_BYTES = 64
 XM_MAX_WORLD = 8
@@ -99,6 +99,7 @@ def load(path: str | None = None):
     lib.xm_comm_disconnect.argtypes = [vp]
     lib.xm_set_q_dense_slab.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
     lib.xm_set_q_dense_slab_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
+    lib.xm_recover.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp, ip]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("xm_default_options", "xm_last_error", "xm_comm_arena"):
@@ -319,6 +320,23 @@ class Handle:
         stats["phase_ms"] = list(st.phase_ms)
         stats["exit"] = EXIT_CODES.get(st.exit_code, str(st.exit_code))
         return primal.value, gt.value, stats
+
+    def recover(self, R, s, Abar=None):
+        """xm_recover: returns dict(R (3 x 3N), s (N,), t (3 x N) / p (3 x M) when Abar is given, eigvals, negative)."""
+        R = _f64(R); s = _f64(np.asarray(s).reshape(-1))
+        n3, r = R.shape
+        N = n3 // 3
+        Ro = np.empty((3, n3), order="F"); so = np.empty(N); eig = np.empty(r); neg = C.c_int()
+        y = None; rows = 0; ab = None
+        if Abar is not None:
+            ab = _f64(Abar); rows = ab.shape[0]
+            y = np.empty((3, rows + 1), order="F")
+        self._check(self.lib.xm_recover(self._h, N, r, _ptr(R), _ptr(s), _ptr(ab) if ab is not None else None, rows, _ptr(Ro), _ptr(so),
+                                        _ptr(y) if y is not None else None, _ptr(eig), C.byref(neg)), "xm_recover")
+        out = dict(R=Ro, s=so, eigvals=eig if r > 3 else None, negative=neg.value, t=None, p=None)
+        if y is not None:
+            out["t"] = y[:, :N]; out["p"] = y[:, N:]
+        return out
 
     def certify(self, R, s, lam, primal):
         R = _f64(R); s = _f64(s)

@@ -123,12 +123,12 @@ extern "C" int xm_comm_init(xm_handle* h, int rank, int world, int n_cameras, in
     XM_CUDA(h, cudaSetDevice(h->device));
     int G = h->opt.grid_ctas > 0 ? h->opt.grid_ctas : h->num_sm;
     G = std::max(1, std::min(std::min(G, h->num_sm), n_cameras / world));
-    const int GT = G * world;
     const size_t n3 = 3 * (size_t)n_cameras, ldq = (n3 + 63) / 64 * 64;
     size_t off = 0;
     h->off_bar = off; off += 256;
     h->off_abort = off; off += 256;
-    h->off_partials = off; off += align_up_sz((size_t)kPartialBufs * (GT + 1) * kPartialStride * sizeof(double), 256);
+    h->off_partials = off; off += align_up_sz((size_t)kPartialBufs * (G + 1) * kPartialStride * sizeof(double), 256);
+    h->off_ll = off; off += align_up_sz((size_t)kPartialBufs * 4 * kMaxWorld * sizeof(unsigned long long), 256);
     h->off_xt = off; off += align_up_sz((size_t)max_r * ldq * sizeof(double), 256);
     h->off_outR = off; off += align_up_sz(n3 * max_r * sizeof(double), 256);
     h->off_outS = off; off += align_up_sz((size_t)n_cameras * sizeof(double), 256);
@@ -401,7 +401,7 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     const size_t N = h->N, n3 = h->n3, ldq = h->ldq;
     const size_t vecR = align_up(n3 * r * sizeof(double), 256), vecS = align_up(N * sizeof(double), 256);
     const size_t total = kNumVecR * vecR + align_up(N * 6 * sizeof(double), 256) + kNumVecS * vecS + align_up((size_t)r * ldq * sizeof(double), 256) +
-                         align_up((size_t)kPartialBufs * (p.GT + 1) * kPartialStride * sizeof(double), 256);
+                         align_up((size_t)kPartialBufs * (p.G + 1) * kPartialStride * sizeof(double), 256);
     bool fresh = false;
     if (h->ws_cap < total) {
         if (h->ws) cudaFree(h->ws);
@@ -430,12 +430,13 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     if (h->world > 1) {       // exchange buffers live in the peer-mapped arenas (same layout on every rank)
         d.Xt = (double*)(h->arena + h->off_xt); d.partials = (double*)(h->arena + h->off_partials);
         d.bar = (unsigned long long*)(h->arena + h->off_bar); d.abort_flag = (int*)(h->arena + h->off_abort);
+        d.ll = (unsigned long long*)(h->arena + h->off_ll);
         for (int w = 0; w < h->world; ++w) {
-            d.Xt_peer[w] = (double*)(h->peer_arena[w] + h->off_xt); d.partials_peer[w] = (double*)(h->peer_arena[w] + h->off_partials);
-            d.bar_peer[w] = (unsigned long long*)(h->peer_arena[w] + h->off_bar); d.abort_peer[w] = (int*)(h->peer_arena[w] + h->off_abort);
+            d.Xt_peer[w] = (double*)(h->peer_arena[w] + h->off_xt); d.ll_peer[w] = (unsigned long long*)(h->peer_arena[w] + h->off_ll);
+            d.abort_peer[w] = (int*)(h->peer_arena[w] + h->off_abort);
         }
     } else {
-        d.Xt_peer[0] = d.Xt; d.partials_peer[0] = d.partials; d.bar_peer[0] = d.bar; d.abort_peer[0] = d.abort_flag;
+        d.Xt_peer[0] = d.Xt; d.abort_peer[0] = d.abort_flag;
     }
     d.vec_smem = p.vec_smem; d.cpc_max = p.cpc; d.profile = h->opt.profile;
     d.nprod = p.nprod; d.NWC = p.NWC;

@@ -52,12 +52,12 @@ struct Dev {
     // multi-GPU camera partition.  The solve runs on world * G CTAs: this rank's CTAs are the global CTAs
     // [g0, g0 + G) of GT and own the cameras (hence the rows of Q) [cam0, cam1).  Only three things cross GPUs, all by
     // peer-mapped stores over NVLink issued from inside the persistent kernel: the Q.Y operand rows a CTA owns (into every
-    // rank's Xt), one double per CTA per reduction (into every rank's slot array) and the barrier arrivals.  world == 1:
+    // rank's Xt), the results (likewise) and one small message per rank pair per barrier (Ctx::grid_sync).  world == 1:
     // every *_peer[0] is the local buffer and all scopes stay .gpu.
     int rank, world, GT, g0, cam0, row0;       // row0 = 3 * cam0: first row of Q held by this rank (dense slab / BSR rows)
     double* Xt_peer[kMaxWorld];
-    double* partials_peer[kMaxWorld];
-    unsigned long long* bar_peer[kMaxWorld];
+    unsigned long long* ll;                    // this GPU's inbox: kPartialBufs x kMaxWorld messages of 4 tagged words
+    unsigned long long* ll_peer[kMaxWorld];    // every rank's inbox (ll_peer[rank] == ll)
     int* abort_peer[kMaxWorld];
     double* outR_peer[kMaxWorld];              // results in the wire layout (3N x r col-major / length N): every CTA stores its
     double* outS_peer[kMaxWorld];              // own cameras into every rank's copy
@@ -78,8 +78,8 @@ struct Dev {
     int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
     int profile;               // fine-grained phase timers on (costs a few percent)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
-    double *partials;          // kPartialBufs * (GT + 1) * kPartialStride             [== partials_peer[rank]]
-    unsigned long long* bar;   // grid barrier counter, monotone                       [== bar_peer[rank]]
+    double *partials;          // kPartialBufs * (G + 1) * kPartialStride: the reduction slots of THIS GPU's CTAs
+    unsigned long long* bar;   // barrier counter of THIS GPU's CTAs, monotone
     int* abort_flag;
     // trust-region call parameters
     double gradtol, ls_step, max_time;
@@ -232,12 +232,21 @@ struct Ctx {
 
     // ---- barrier over all GT = world * G CTAs fused with a deterministic all-reduce (the CTAs of a rank are co-resident:
     // cooperative launch; the ranks' kernels run concurrently).
-    // Arrival: this CTA's partial sum into its slot of EVERY rank's slot array, release fence, one RED.add on EVERY rank's
-    // monotone counter (peer-mapped memory: the stores and the atomics travel over NVLink; world == 1: one local slot, one
-    // local RED, .gpu scope).  Thread 0 spins on the LOCAL counter; once it shows GT arrivals warp 0 reads all GT slots from
-    // local memory and adds them in slot order: identical bits in every CTA of every rank, run to run.  (Measured single-GPU
-    // alternatives — all-to-all slot polling with tagged values, with or without the counter — were slower: the polling
-    // traffic on ~20 hot lines outweighs the saved round trip; profiles/r01_barrier_variants.txt.)
+    //
+    // world == 1.  Arrival: release fence, this CTA's partial sum into its slot, one RED.add on a monotone counter.  Thread 0
+    // spins on the counter (one hot line, 148 pollers); once it is complete warp 0 reads all slots (one more L2 round trip)
+    // and adds them in slot order: identical bits in every CTA, run to run.  2.1 us on 148 CTAs.  (Measured alternatives —
+    // all-to-all slot polling with tagged values, with or without the counter — were slower: the polling traffic on ~20 hot
+    // lines outweighs the saved round trip; profiles/r01_barrier_variants.txt.)
+    //
+    // world > 1: two levels.  Every CTA arrives on its OWN GPU's counter as above, after a system-scope fence (its operand
+    // rows / results went into peer memory over NVLink and must have landed).  CTA 0 of each rank is the rank's leader: it
+    // waits for the G local arrivals, adds the rank's G slots in slot order and sends ONE message (rank sum, flag) to every
+    // rank as four 8-byte words that each carry 32 payload bits and the 32-bit epoch as a tag (a store of 8 bytes is single-
+    // copy atomic, so no fence and no second flag store: the latency is one NVLink hop).  Every CTA of every rank polls the
+    // `world` messages in its own GPU's memory and adds the rank sums in rank order: identical bits everywhere.  (The first
+    // version let all world * G CTAs write slots and RED.add to every GPU directly: 12 us per barrier at 2 GPUs — same-address
+    // atomics arriving over NVLink serialise — against ~4 us for this one; profiles/r01_multi_gpu.md.)
     double pend_v, pend_f;
     __device__ __forceinline__ void publish(double v, double flag = 0.0) {
         v = warpsum(v);
@@ -252,77 +261,107 @@ struct Ctx {
     __device__ __forceinline__ void raise_abort() {
         for (int w = 0; w < d.world; ++w) *(volatile int*)d.abort_peer[w] = 1;
     }
+    // warp 0: fixed-order sum of the first `n` slots; the flag sits in slot n.  Every lane returns the totals.
+    __device__ __forceinline__ void sum_slots(const double* slots, int n, double& acc_out, double& flag_out) {
+        constexpr int MAXS = 5;                                              // slots per lane and pass; one pass when n + 1 <= 160
+        double acc = 0.0, f0 = 0.0;
+#pragma unroll 1
+        for (int base = 0; base <= n; base += 32 * MAXS) {
+            double w[MAXS];
+#pragma unroll
+            for (int q = 0; q < MAXS; ++q) {                                 // independent loads: one L2 round trip per pass
+                const int sl = base + lane + 32 * q;
+                w[q] = (sl <= n) ? __ldcg(slots + sl) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < MAXS; ++q) {                                 // fixed slot order per lane
+                const int sl = base + lane + 32 * q;
+                if (sl < n) acc += w[q];
+                if (sl == n) f0 = w[q];
+            }
+        }
+        acc_out = warpsum(acc);
+        flag_out = warpsum(f0);                                              // exactly one lane holds the flag, the rest add 0
+    }
     __device__ __forceinline__ bool grid_sync() {
         __syncthreads();
         epoch += 1;                                           // uniform in every thread of every CTA of every rank
         if (warp == 0) {
-            unsigned long long t0 = 0;
-            if (tid == 0) t0 = gtimer();
-            const int GT = d.GT;
-            const size_t soff = (size_t)pbuf * (GT + 1);
-            const double* slots = d.partials + soff;
-            const unsigned long long target = epoch * (unsigned long long)GT;
+            unsigned long long t0 = gtimer();
+            const int G = d.G;
+            const size_t soff = (size_t)pbuf * (G + 1);
+            const double* slots = d.partials + soff;          // this GPU's CTAs only
+            const unsigned long long target = epoch * (unsigned long long)G;
+            const bool multi = d.world > 1;
             int ok = 1;
             if (tid == 0) {
-                unsigned spins = 0;
-                if (d.world == 1) {
-                    d.partials[soff + gc] = pend_v;
-                    if (gc == 0) d.partials[soff + GT] = pend_f;                // global CTA 0's flag rides in the extra slot GT
-                    asm volatile("fence.acq_rel.gpu;" ::: "memory");            // release everything this CTA wrote
-                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(d.bar) : "memory");
+                d.partials[soff + blockIdx.x] = pend_v;
+                if (gc == 0) d.partials[soff + G] = pend_f;                     // global CTA 0's flag rides in the extra slot G
+                // release everything this CTA wrote — at system scope when peers are involved: the operand rows / results the
+                // CTA's threads stored into peer memory before the __syncthreads above are visible there before the arrival
+                if (multi) asm volatile("fence.acq_rel.sys;" ::: "memory");
+                else       asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(d.bar) : "memory");
+                pend_v = 0.0; pend_f = 0.0;
+                if (!multi || blockIdx.x == 0) {                                // multi-GPU: only the rank's leader needs the count
+                    unsigned spins = 0;
 #pragma unroll 1
                     while (ld_acquire_gpu_u64(d.bar) < target) {
                         if ((++spins & 0x3ffu) == 0) {
                             if (*(volatile int*)d.abort_flag) { ok = 0; break; }
-                            if (gtimer() - t0 > 4000000000ull) { *(volatile int*)d.abort_flag = 1; ok = 0; break; }
+                            // multi-GPU: generous — the ranks' hosts launch independently (a peer may reach its launch seconds later)
+                            if (gtimer() - t0 > (multi ? 30000000000ull : 4000000000ull)) { raise_abort(); ok = 0; break; }
                         }
                     }
                     asm volatile("fence.acq_rel.gpu;" ::: "memory");            // acquire
-                } else {
-#pragma unroll 1
-                    for (int w = 0; w < d.world; ++w) {
-                        d.partials_peer[w][soff + gc] = pend_v;
-                        if (gc == 0) d.partials_peer[w][soff + GT] = pend_f;
+                }
+            }
+            __syncwarp();
+            double acc = 0.0, f0 = 0.0;
+            if (!multi) {
+                sum_slots(slots, G, acc, f0);
+            } else {
+                const unsigned tag = (unsigned)(epoch & 0xffffffffull);
+                const int nw = 4 * d.world;                                      // 4 words per message: sum lo/hi, flag lo/hi
+                unsigned long long* inbox = d.ll + (size_t)pbuf * (4 * kMaxWorld);
+                if (blockIdx.x == 0) {                                           // leader: this rank's sum to every rank
+                    double racc, rf0;
+                    sum_slots(slots, G, racc, rf0);
+                    if (lane < nw) {
+                        const int w = lane >> 2, k = lane & 3;
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(k < 2 ? racc : rf0);
+                        const unsigned long long word = ((unsigned long long)tag << 32) | ((k & 1) ? (bits >> 32) : (bits & 0xffffffffull));
+                        unsigned long long* dst = d.ll_peer[w] + (size_t)pbuf * (4 * kMaxWorld) + 4 * d.rank + k;
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
                     }
-                    // system-scope release: the operand rows / results the CTA's threads stored into peer memory before the
-                    // __syncthreads above, and the slots, are visible on every GPU before the arrivals below
-                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                }
+                unsigned long long word = 0;
+                if (lane < nw) {                                                 // every CTA: wait for the `world` messages
+                    unsigned spins = 0;
 #pragma unroll 1
-                    for (int w = 0; w < d.world; ++w)
-                        asm volatile("red.relaxed.sys.global.add.u64 [%0], 1;" ::"l"(d.bar_peer[w]) : "memory");
-#pragma unroll 1
-                    while (ld_acquire_sys_u64(d.bar) < target) {
+                    for (;;) {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(inbox + lane) : "memory");
+                        if ((unsigned)(word >> 32) == tag) break;
                         if ((++spins & 0x3ffu) == 0) {
                             if (*(volatile int*)d.abort_flag) { ok = 0; break; }
-                            // generous: the ranks' hosts launch independently (a peer may reach its launch seconds later)
                             if (gtimer() - t0 > 30000000000ull) { raise_abort(); ok = 0; break; }
                         }
                     }
-                    asm volatile("fence.acq_rel.sys;" ::: "memory");
                 }
-                pend_v = 0.0; pend_f = 0.0;
-            }
-            __syncwarp();
-            constexpr int MAXS = 5;                                          // slots per lane and pass; one pass when GT + 1 <= 160
-            double acc = 0.0, f0 = 0.0;
+                __syncwarp();
+                if (lane == 0) asm volatile("fence.acq_rel.sys;" ::: "memory"); // acquire: what the peers stored before arriving
+                const unsigned lo32 = (unsigned)(word & 0xffffffffull);
 #pragma unroll 1
-            for (int base = 0; base <= GT; base += 32 * MAXS) {
-                double w[MAXS];
-#pragma unroll
-                for (int q = 0; q < MAXS; ++q) {                             // independent loads: one L2 round trip per pass
-                    const int sl = base + lane + 32 * q;
-                    w[q] = (sl <= GT) ? __ldcg(slots + sl) : 0.0;
-                }
-#pragma unroll
-                for (int q = 0; q < MAXS; ++q) {                             // fixed slot order per lane
-                    const int sl = base + lane + 32 * q;
-                    if (sl < GT) acc += w[q];
-                    if (sl == GT) f0 = w[q];
+                for (int w = 0; w < d.world; ++w) {                              // rank order: identical bits on every GPU
+                    const unsigned a0 = __shfl_sync(0xffffffffu, lo32, 4 * w), a1 = __shfl_sync(0xffffffffu, lo32, 4 * w + 1);
+                    acc += __longlong_as_double((long long)(((unsigned long long)a1 << 32) | a0));
+                    if (w == 0) {
+                        const unsigned b0 = __shfl_sync(0xffffffffu, lo32, 2), b1 = __shfl_sync(0xffffffffu, lo32, 3);
+                        f0 = __longlong_as_double((long long)(((unsigned long long)b1 << 32) | b0));
+                    }
                 }
             }
-            acc = warpsum(acc);
-            f0 = warpsum(f0);                                                // exactly one lane holds the flag, the rest add 0
-            ok = __shfl_sync(0xffffffffu, ok, 0);
+            ok = __all_sync(0xffffffffu, ok);
             if (lane == 0) { bcast[0] = acc; bcast[1] = f0; bcast[3] = ok ? 1.0 : 0.0; }
             if (tid == 0) t_sync += gtimer() - t0;
         }
