@@ -133,7 +133,8 @@ int  xm_qy_dev(xm_handle* h, int r, double alpha, const double* X_dev, double* o
 /* Measurement hook: average device time (ms, CUDA events on the handle's stream) of `iters` back-to-back launches of
  * the Q.Y kernel on the operand left in the workspace by the last xm_qy/xm_qy_dev call. */
 int  xm_bench_qy(xm_handle* h, int r, int iters, double* avg_ms);   /* iters < 0: grid barrier after every product */
-int  xm_bench_barrier(xm_handle* h, int r, int iters, double* avg_us);
+int  xm_bench_barrier(xm_handle* h, int r, int iters, double* avg_us);   /* iters < 0: |iters| x (barrier + operand exchange) */
+int  xm_debug_counters(xm_handle* h, unsigned long long* out8);  /* raw ns counters of the last launch (profile = 1) */
 int  xm_debug_trace(xm_handle* h, unsigned long long* out256);   /* (tag, ns) pairs of the last profiled solve */
 
 /* Mirrors XMtrustregion.  R0/R_out: 3N x r col-major; s0/s_out: length N (s[0] = 1); v: length 3N or NULL when

@@ -43,7 +43,7 @@ EXPORTS = [
     "xm_op_objective", "xm_op_rgrad", "xm_op_rhess", "xm_op_retract", "xm_certify", "xm_escape_scale", "xm_bench_qy",
     "xm_bench_barrier", "xm_debug_trace",
     "xm_partition", "xm_comm_init", "xm_comm_connect", "xm_comm_connect_ptrs", "xm_comm_arena", "xm_comm_info", "xm_comm_reset", "xm_comm_disconnect",
-    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover",
+    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover", "xm_debug_counters",
 ]
 XM_IPC_HANDLE_BYTES = 64
 XM_MAX_WORLD = 8
@@ -87,6 +87,7 @@ def load(path: str | None = None):
     lib.xm_bench_qy.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.xm_bench_barrier.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.xm_debug_trace.argtypes = [vp, vp]
+    lib.xm_debug_counters.argtypes = [vp, vp]
     ip = C.POINTER(C.c_int)
     lib.xm_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
     lib.xm_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
@@ -258,6 +259,11 @@ class Handle:
         self._check(self.lib.xm_debug_trace(self._h, C.cast(buf, C.c_void_p)), "xm_debug_trace")
         out = [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(128) if buf[2 * i + 1]]
         return out
+
+    def debug_counters(self):
+        buf = (C.c_ulonglong * 8)()
+        self._check(self.lib.xm_debug_counters(self._h, C.cast(buf, C.c_void_p)), "xm_debug_counters")
+        return [int(x) for x in buf]
 
     def bench_barrier(self, r: int, iters: int) -> float:
         us = C.c_double()

@@ -3,6 +3,7 @@
 #include "xm_host.h"
 #include "xm_solve.cuh"
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,7 +130,9 @@ extern "C" int xm_comm_init(xm_handle* h, int rank, int world, int n_cameras, in
     h->off_abort = off; off += 256;
     h->off_partials = off; off += align_up_sz((size_t)kPartialBufs * (G + 1) * kPartialStride * sizeof(double), 256);
     h->off_ll = off; off += align_up_sz((size_t)kPartialBufs * 4 * kMaxWorld * sizeof(unsigned long long), 256);
+    h->off_slots = off; off += align_up_sz((size_t)kPartialBufs * G * sizeof(ulonglong2), 256);
     h->off_xt = off; off += align_up_sz((size_t)max_r * ldq * sizeof(double), 256);
+    h->off_xtll = off; off += align_up_sz((size_t)max_r * ldq * sizeof(ulonglong2), 256);
     h->off_outR = off; off += align_up_sz(n3 * max_r * sizeof(double), 256);
     h->off_outS = off; off += align_up_sz((size_t)n_cameras * sizeof(double), 256);
     if (cudaMalloc(&h->arena, off) != cudaSuccess) { cudaGetLastError(); h->arena = nullptr; h->err = "communicator arena cudaMalloc failed"; return XM_ENOMEM; }
@@ -223,7 +226,7 @@ extern "C" int xm_comm_reset(xm_handle* h) {
     if (!h || !h->arena) return XM_EINVAL;
     XM_CUDA(h, cudaSetDevice(h->device));
     XM_CUDA(h, cudaDeviceSynchronize());
-    XM_CUDA(h, cudaMemset(h->arena, 0, h->off_xt));          // counter, abort flag, reduction slots
+    XM_CUDA(h, cudaMemset(h->arena, 0, h->arena_bytes));     // counters, abort flag, every tagged word
     XM_CUDA(h, cudaMemset(h->d_bar, 0, 256));
     XM_CUDA(h, cudaDeviceSynchronize());
     h->comm_broken = false;
@@ -431,8 +434,11 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         d.Xt = (double*)(h->arena + h->off_xt); d.partials = (double*)(h->arena + h->off_partials);
         d.bar = (unsigned long long*)(h->arena + h->off_bar); d.abort_flag = (int*)(h->arena + h->off_abort);
         d.ll = (unsigned long long*)(h->arena + h->off_ll);
+        d.slots_ll = (ulonglong2*)(h->arena + h->off_slots); d.XtLL = (ulonglong2*)(h->arena + h->off_xtll);
+        d.nown = 3 * (h->cam1 - h->cam0);
         for (int w = 0; w < h->world; ++w) {
             d.Xt_peer[w] = (double*)(h->peer_arena[w] + h->off_xt); d.ll_peer[w] = (unsigned long long*)(h->peer_arena[w] + h->off_ll);
+            d.XtLL_peer[w] = (ulonglong2*)(h->peer_arena[w] + h->off_xtll);
             d.abort_peer[w] = (int*)(h->peer_arena[w] + h->off_abort);
         }
     } else {
@@ -588,9 +594,10 @@ extern "C" int xm_bench_barrier(xm_handle* h, int r, int iters, double* avg_us) 
     Plan p;
     int rc = prepare(h, r, &p);
     if (rc) return rc;
-    if (!avg_us || iters <= 0) return XM_EINVAL;
+    if (!avg_us || iters == 0) return XM_EINVAL;
     Dev d = h->dev;
-    d.op_repeat = iters;
+    d.op_repeat = iters;          // negative: |iters| barriers followed by |iters| operand exchanges (push, unpack, operand_sync)
+    if (iters < 0) iters = -iters;
     cudaEvent_t e0, e1;
     XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
     (void)bind_out(h, d, h->io_Rout, h->io_sout);
@@ -748,6 +755,14 @@ extern "C" int xm_op_retract(xm_handle* h, int r, const double* R, const double*
                              double lr, double* Rn, double* sn) {
     if (!etaR || !etas) return XM_EINVAL;
     return op_common(h, r, 4, R, s, 0.0, etaR, etas, lr, Rn, sn, nullptr);
+}
+
+// debug: the 8 raw counters DevStats.dbg left on the device by the last launch (ns; meaning depends on the kernel/opcode)
+extern "C" int xm_debug_counters(xm_handle* h, unsigned long long* out8) {
+    if (!h || !out8) return XM_EINVAL;
+    XM_CUDA(h, cudaSetDevice(h->device));
+    XM_CUDA(h, cudaMemcpy(out8, (const char*)h->d_stats + offsetof(DevStats, dbg), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return XM_OK;
 }
 
 // debug: (tag, ns) pairs recorded by the last profiled solve (opt.profile = 1); out must hold 256 entries

@@ -58,11 +58,16 @@ struct Dev {
     double* Xt_peer[kMaxWorld];
     unsigned long long* ll;                    // this GPU's inbox: kPartialBufs x kMaxWorld messages of 4 tagged words
     unsigned long long* ll_peer[kMaxWorld];    // every rank's inbox (ll_peer[rank] == ll)
+    ulonglong2* slots_ll;                      // this GPU's CTAs' tagged partial sums: kPartialBufs x G
+    ulonglong2* XtLL;                          // this GPU's staging copy of the operand rows owned by peers (tagged, 16 B per double)
+    ulonglong2* XtLL_peer[kMaxWorld];
+    int nown;                                  // rows of the operand this rank owns: 3 * (cam1 - cam0), starting at row0
     int* abort_peer[kMaxWorld];
     double* outR_peer[kMaxWorld];              // results in the wire layout (3N x r col-major / length N): every CTA stores its
     double* outS_peer[kMaxWorld];              // own cameras into every rank's copy
-    unsigned long long* epoch_store;           // local: barrier epoch carried from launch to launch (the counters are never reset
-                                               // while a communicator is live: a peer may already be arriving for the next launch)
+    unsigned long long* epoch_store;           // local, 3 words carried from launch to launch: barrier epoch, local-barrier epoch,
+                                               // operand tag (the counters / tags are never reset while a communicator is live:
+                                               // a peer may already be arriving for the next launch)
     // dense Q.Y through a shared-memory ring fed by 2-D tensor-map TMA (use_tma) or by direct streaming loads
     int use_tma, KC, ST, nbmax, nchunks, stage_doubles;
     int l2_prefetch;           // Q chunks (beyond the ring) prefetched into L2 at the end of a Q.Y phase
@@ -185,10 +190,13 @@ struct Ctx {
     int gc;                     // global CTA index in [0, GT): rank * G + blockIdx.x
     int cam_lo, cam_hi;         // cameras owned by this CTA
     unsigned long long epoch, epoch_begin;   // barrier epoch (monotone across launches)
+    unsigned long long lepoch;               // local-barrier epoch (multi-GPU)
+    unsigned xtag;                           // tag of the current operand push (multi-GPU)
     int pbuf;                   // rotating partial buffer
     bool aborted;
     unsigned long long t_qy, t_sync;   // accumulated by CTA 0 thread 0
     unsigned long long dbg0, dbg1, dbg2, dbg3;
+    unsigned long long bseg[5];        // profile: thread 0's time in the segments of the multi-GPU barrier
     int trace_n; bool trace_on;
     __device__ __forceinline__ void tr(int tag) {
         if (trace_on && trace_n < 127) { d.stats->trace[2 * trace_n] = (unsigned long long)tag; d.stats->trace[2 * trace_n + 1] = gtimer(); ++trace_n; }
@@ -217,8 +225,10 @@ struct Ctx {
         // barrier epoch continues where the previous launch on this communicator stopped (identical on every rank: all
         // ranks run the same number of barriers per launch); the host zeroes it together with the counter when world == 1
         epoch = __ldcg(d.epoch_store); epoch_begin = epoch;
+        lepoch = __ldcg(d.epoch_store + 1); xtag = (unsigned)__ldcg(d.epoch_store + 2);
         pbuf = (int)(epoch % (unsigned long long)kPartialBufs);
         aborted = false; pend_v = 0.0; pend_f = 0.0; t_qy = 0; t_sync = 0; dbg0 = dbg1 = dbg2 = dbg3 = 0; trace_n = 0; trace_on = false;
+        for (int q = 0; q < 5; ++q) bseg[q] = 0;
         red = red_; bsum = bsum_; bcast = bcast_;
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
@@ -227,7 +237,7 @@ struct Ctx {
     // end of a launch: remember the epoch for the next one (every CTA has long read epoch_store by now: it sits behind at
     // least one barrier whenever the value changes)
     __device__ __forceinline__ void save_epoch() {
-        if (blockIdx.x == 0 && tid == 0 && epoch != epoch_begin) *d.epoch_store = epoch;
+        if (blockIdx.x == 0 && tid == 0 && epoch != epoch_begin) { d.epoch_store[0] = epoch; d.epoch_store[1] = lepoch; d.epoch_store[2] = xtag; }
     }
 
     // ---- barrier over all GT = world * G CTAs fused with a deterministic all-reduce (the CTAs of a rank are co-resident:
@@ -239,14 +249,19 @@ struct Ctx {
     // all-to-all slot polling with tagged values, with or without the counter — were slower: the polling traffic on ~20 hot
     // lines outweighs the saved round trip; profiles/r01_barrier_variants.txt.)
     //
-    // world > 1: two levels.  Every CTA arrives on its OWN GPU's counter as above, after a system-scope fence (its operand
-    // rows / results went into peer memory over NVLink and must have landed).  CTA 0 of each rank is the rank's leader: it
-    // waits for the G local arrivals, adds the rank's G slots in slot order and sends ONE message (rank sum, flag) to every
-    // rank as four 8-byte words that each carry 32 payload bits and the 32-bit epoch as a tag (a store of 8 bytes is single-
-    // copy atomic, so no fence and no second flag store: the latency is one NVLink hop).  Every CTA of every rank polls the
-    // `world` messages in its own GPU's memory and adds the rank sums in rank order: identical bits everywhere.  (The first
-    // version let all world * G CTAs write slots and RED.add to every GPU directly: 12 us per barrier at 2 GPUs — same-address
-    // atomics arriving over NVLink serialise — against ~4 us for this one; profiles/r01_multi_gpu.md.)
+    // world > 1: two levels, and NO system-scope fence on the iteration path — fence.acq_rel.sys costs 3.5-4 us on B200 even
+    // with nothing outstanding (profiles/r01_multi_gpu.md), more than the rest of the barrier.  Everything that crosses a
+    // GPU boundary carries its own validity tag instead (the "LL" idea: an 8-byte store is single-copy atomic, so a word of
+    // 32 payload bits + a 32-bit tag needs neither a fence nor a separate flag; latency = one NVLink hop):
+    //   * every CTA: release fence at .gpu scope, then its partial sum as two tagged words into its slot in LOCAL memory;
+    //   * CTA 0 of each rank (the leader): warp 0 polls the rank's G slots (5 per lane) until all carry this epoch's tag,
+    //     adds them in slot order and sends ONE message (rank sum, flag) = four tagged words to every rank's inbox;
+    //   * every CTA of every rank polls the `world` messages in its own GPU's inbox and adds the rank sums in rank order:
+    //     identical bits everywhere.
+    // Bulk data that crosses GPUs (the operand rows) is tagged the same way and polled by its consumers (st_operand /
+    // unpack_operand below), so the barriers never have to publish remote stores.  The one exception, `remote_data`, is the
+    // last barrier of a launch: results were pushed into the peers' output copies with plain stores and the hosts read
+    // them next, so there the arrival fence is .sys (once per launch).
     double pend_v, pend_f;
     __device__ __forceinline__ void publish(double v, double flag = 0.0) {
         v = warpsum(v);
@@ -260,6 +275,14 @@ struct Ctx {
     }
     __device__ __forceinline__ void raise_abort() {
         for (int w = 0; w < d.world; ++w) *(volatile int*)d.abort_peer[w] = 1;
+    }
+    // bounded spin helper: false = give up (abort flag seen or watchdog fired)
+    __device__ __forceinline__ bool spin_ok(unsigned& spins, unsigned long long t0) {
+        if ((++spins & 0x3ffu) != 0) return true;
+        if (*(volatile int*)d.abort_flag) return false;
+        // multi-GPU: generous — the ranks' hosts launch independently (a peer may reach its launch seconds later)
+        if (gtimer() - t0 > (d.world > 1 ? 30000000000ull : 4000000000ull)) { raise_abort(); return false; }
+        return true;
     }
     // warp 0: fixed-order sum of the first `n` slots; the flag sits in slot n.  Every lane returns the totals.
     __device__ __forceinline__ void sum_slots(const double* slots, int n, double& acc_out, double& flag_out) {
@@ -283,84 +306,115 @@ struct Ctx {
         acc_out = warpsum(acc);
         flag_out = warpsum(f0);                                              // exactly one lane holds the flag, the rest add 0
     }
-    __device__ __forceinline__ bool grid_sync() {
+    static __device__ __forceinline__ void st_tagged(ulonglong2* dst, double v, unsigned tag) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v), tg = (unsigned long long)tag << 32;
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(tg | (bits & 0xffffffffull)), "l"(tg | (bits >> 32)) : "memory");
+    }
+    // one 16-byte load of a tagged double; true when both halves carry `tag`
+    static __device__ __forceinline__ bool ld_tagged(const ulonglong2* src, unsigned tag, double& v) {
+        unsigned long long a, b;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+        v = __longlong_as_double((long long)((b << 32) | (a & 0xffffffffull)));
+        return (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
+    }
+
+    __device__ __forceinline__ void barrier_single(int& ok, double& acc, double& f0, unsigned long long t0) {
+        const int G = d.G;
+        const size_t soff = (size_t)pbuf * (G + 1);
+        if (tid == 0) {
+            d.partials[soff + blockIdx.x] = pend_v;
+            if (blockIdx.x == 0) d.partials[soff + G] = pend_f;                 // CTA 0's flag rides in the extra slot G
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");                    // release everything this CTA wrote
+            asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(d.bar) : "memory");
+            const unsigned long long target = epoch * (unsigned long long)G;
+            unsigned spins = 0;
+#pragma unroll 1
+            while (ld_acquire_gpu_u64(d.bar) < target) if (!spin_ok(spins, t0)) { ok = 0; break; }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");                    // acquire
+        }
+        __syncwarp();
+        sum_slots(d.partials + soff, G, acc, f0);
+    }
+    __device__ __forceinline__ void barrier_multi(int& ok, double& acc, double& f0, unsigned long long t0, bool remote_data) {
+        const int G = d.G;
+        const unsigned tag = (unsigned)(epoch & 0xffffffffull);
+        ulonglong2* slots = d.slots_ll + (size_t)pbuf * G;                      // this GPU's CTAs only, tagged
+        unsigned long long tseg = t0;
+        double my_flag = 0.0;
+        if (tid == 0) {
+            if (remote_data) asm volatile("fence.acq_rel.sys;" ::: "memory");   // plain stores into peer memory must have landed
+            else             asm volatile("fence.acq_rel.gpu;" ::: "memory");   // release what this CTA wrote (local consumers)
+            st_tagged(slots + blockIdx.x, pend_v, tag);
+            my_flag = pend_f;
+            if (d.profile) { const unsigned long long t = gtimer(); bseg[0] += t - t0; tseg = t; }
+        }
+        __syncwarp();
+        const int nw = 4 * d.world;                                              // 4 words per message: sum lo/hi, flag lo/hi
+        unsigned long long* inbox = d.ll + (size_t)pbuf * (4 * kMaxWorld);
+        if (blockIdx.x == 0) {                                                   // leader: gather the rank's slots as they arrive
+            constexpr int MAXS = 5;
+            double racc = 0.0;
+#pragma unroll 1
+            for (int base = 0; base < G; base += 32 * MAXS) {
+                double w[MAXS];
+#pragma unroll
+                for (int q = 0; q < MAXS; ++q) {
+                    const int sl = base + lane + 32 * q;
+                    w[q] = 0.0;
+                    if (sl < G) {
+                        unsigned spins = 0;
+#pragma unroll 1
+                        while (!ld_tagged(slots + sl, tag, w[q])) if (!spin_ok(spins, t0)) { ok = 0; w[q] = 0.0; break; }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < MAXS; ++q) racc += w[q];                    // fixed slot order per lane
+            }
+            racc = warpsum(racc);
+            const double rf0 = __shfl_sync(0xffffffffu, my_flag, 0);            // only rank 0's flag is used (global CTA 0's clock)
+            if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[1] += t - tseg; tseg = t; }
+            if (lane < nw) {
+                const int w = lane >> 2, k = lane & 3;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(k < 2 ? racc : rf0);
+                const unsigned long long word = ((unsigned long long)tag << 32) | ((k & 1) ? (bits >> 32) : (bits & 0xffffffffull));
+                unsigned long long* dst = d.ll_peer[w] + (size_t)pbuf * (4 * kMaxWorld) + 4 * d.rank + k;
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+            }
+        }
+        unsigned long long word = 0;
+        if (lane < nw) {                                                         // every CTA: wait for the `world` messages
+            unsigned spins = 0;
+#pragma unroll 1
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(inbox + lane) : "memory");
+                if ((unsigned)(word >> 32) == tag) break;
+                if (!spin_ok(spins, t0)) { ok = 0; break; }
+            }
+        }
+        __syncwarp();
+        if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[3] += t - tseg; tseg = t; }
+        // acquire what this GPU's CTAs wrote before they arrived (plain stores, consumed after the barrier through L1 / TMA)
+        if (lane == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[4] += t - tseg; }
+        const unsigned lo32 = (unsigned)(word & 0xffffffffull);
+#pragma unroll 1
+        for (int w = 0; w < d.world; ++w) {                                      // rank order: identical bits on every GPU
+            const unsigned a0 = __shfl_sync(0xffffffffu, lo32, 4 * w), a1 = __shfl_sync(0xffffffffu, lo32, 4 * w + 1);
+            acc += __longlong_as_double((long long)(((unsigned long long)a1 << 32) | a0));
+        }
+        const unsigned b0 = __shfl_sync(0xffffffffu, lo32, 2), b1 = __shfl_sync(0xffffffffu, lo32, 3);
+        f0 = __longlong_as_double((long long)(((unsigned long long)b1 << 32) | b0));
+    }
+    __device__ __forceinline__ bool grid_sync(bool remote_data = false) {
         __syncthreads();
         epoch += 1;                                           // uniform in every thread of every CTA of every rank
         if (warp == 0) {
-            unsigned long long t0 = gtimer();
-            const int G = d.G;
-            const size_t soff = (size_t)pbuf * (G + 1);
-            const double* slots = d.partials + soff;          // this GPU's CTAs only
-            const unsigned long long target = epoch * (unsigned long long)G;
-            const bool multi = d.world > 1;
-            int ok = 1;
-            if (tid == 0) {
-                d.partials[soff + blockIdx.x] = pend_v;
-                if (gc == 0) d.partials[soff + G] = pend_f;                     // global CTA 0's flag rides in the extra slot G
-                // release everything this CTA wrote — at system scope when peers are involved: the operand rows / results the
-                // CTA's threads stored into peer memory before the __syncthreads above are visible there before the arrival
-                if (multi) asm volatile("fence.acq_rel.sys;" ::: "memory");
-                else       asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(d.bar) : "memory");
-                pend_v = 0.0; pend_f = 0.0;
-                if (!multi || blockIdx.x == 0) {                                // multi-GPU: only the rank's leader needs the count
-                    unsigned spins = 0;
-#pragma unroll 1
-                    while (ld_acquire_gpu_u64(d.bar) < target) {
-                        if ((++spins & 0x3ffu) == 0) {
-                            if (*(volatile int*)d.abort_flag) { ok = 0; break; }
-                            // multi-GPU: generous — the ranks' hosts launch independently (a peer may reach its launch seconds later)
-                            if (gtimer() - t0 > (multi ? 30000000000ull : 4000000000ull)) { raise_abort(); ok = 0; break; }
-                        }
-                    }
-                    asm volatile("fence.acq_rel.gpu;" ::: "memory");            // acquire
-                }
-            }
-            __syncwarp();
+            const unsigned long long t0 = gtimer();
+            int ok = aborted ? 0 : 1;
             double acc = 0.0, f0 = 0.0;
-            if (!multi) {
-                sum_slots(slots, G, acc, f0);
-            } else {
-                const unsigned tag = (unsigned)(epoch & 0xffffffffull);
-                const int nw = 4 * d.world;                                      // 4 words per message: sum lo/hi, flag lo/hi
-                unsigned long long* inbox = d.ll + (size_t)pbuf * (4 * kMaxWorld);
-                if (blockIdx.x == 0) {                                           // leader: this rank's sum to every rank
-                    double racc, rf0;
-                    sum_slots(slots, G, racc, rf0);
-                    if (lane < nw) {
-                        const int w = lane >> 2, k = lane & 3;
-                        const unsigned long long bits = (unsigned long long)__double_as_longlong(k < 2 ? racc : rf0);
-                        const unsigned long long word = ((unsigned long long)tag << 32) | ((k & 1) ? (bits >> 32) : (bits & 0xffffffffull));
-                        unsigned long long* dst = d.ll_peer[w] + (size_t)pbuf * (4 * kMaxWorld) + 4 * d.rank + k;
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-                    }
-                }
-                unsigned long long word = 0;
-                if (lane < nw) {                                                 // every CTA: wait for the `world` messages
-                    unsigned spins = 0;
-#pragma unroll 1
-                    for (;;) {
-                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(inbox + lane) : "memory");
-                        if ((unsigned)(word >> 32) == tag) break;
-                        if ((++spins & 0x3ffu) == 0) {
-                            if (*(volatile int*)d.abort_flag) { ok = 0; break; }
-                            if (gtimer() - t0 > 30000000000ull) { raise_abort(); ok = 0; break; }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) asm volatile("fence.acq_rel.sys;" ::: "memory"); // acquire: what the peers stored before arriving
-                const unsigned lo32 = (unsigned)(word & 0xffffffffull);
-#pragma unroll 1
-                for (int w = 0; w < d.world; ++w) {                              // rank order: identical bits on every GPU
-                    const unsigned a0 = __shfl_sync(0xffffffffu, lo32, 4 * w), a1 = __shfl_sync(0xffffffffu, lo32, 4 * w + 1);
-                    acc += __longlong_as_double((long long)(((unsigned long long)a1 << 32) | a0));
-                    if (w == 0) {
-                        const unsigned b0 = __shfl_sync(0xffffffffu, lo32, 2), b1 = __shfl_sync(0xffffffffu, lo32, 3);
-                        f0 = __longlong_as_double((long long)(((unsigned long long)b1 << 32) | b0));
-                    }
-                }
-            }
+            if (d.world == 1) barrier_single(ok, acc, f0, t0);
+            else              barrier_multi(ok, acc, f0, t0, remote_data);
+            if (tid == 0) { pend_v = 0.0; pend_f = 0.0; }
             ok = __all_sync(0xffffffffu, ok);
             if (lane == 0) { bcast[0] = acc; bcast[1] = f0; bcast[3] = ok ? 1.0 : 0.0; }
             if (tid == 0) t_sync += gtimer() - t0;
@@ -369,6 +423,59 @@ struct Ctx {
         pbuf = (pbuf + 1) % kPartialBufs;
         if (bcast[3] == 0.0) { aborted = true; return false; }
         return true;
+    }
+    // barrier over THIS GPU's CTAs only (multi-GPU runs: after the operand rows of the peers have been unpacked)
+    __device__ __forceinline__ bool local_sync() {
+        __syncthreads();
+        lepoch += 1;
+        if (tid == 0) {
+            const unsigned long long t0 = gtimer();
+            int ok = aborted ? 0 : 1;
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(d.bar) : "memory");
+            const unsigned long long target = lepoch * (unsigned long long)d.G;
+            unsigned spins = 0;
+#pragma unroll 1
+            while (ld_acquire_gpu_u64(d.bar) < target) if (!spin_ok(spins, t0)) { ok = 0; break; }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            bcast[3] = ok ? 1.0 : 0.0;
+            t_sync += gtimer() - t0;
+        }
+        __syncthreads();
+        if (bcast[3] == 0.0) { aborted = true; return false; }
+        return true;
+    }
+
+    // ---- multi-GPU operand exchange.  A phase that builds the Q.Y operand calls begin_push() once (new tag), stores its own
+    // cameras' rows with st_operand() (plain into the local Xt, tagged into every peer's staging copy XtLL) and is followed —
+    // before the next barrier of any kind — by unpack_operand(): the CTAs of a rank share out the rows owned by the other
+    // ranks, poll their tagged words as they land and write them plainly into the local Xt.  The barrier that follows
+    // (operand_sync(): a local one; or the cross-GPU reduction that was due anyway) publishes them to the local consumers.
+    __device__ __forceinline__ void begin_push() { xtag += 1; }
+    __device__ __forceinline__ void unpack_operand() {
+        if (d.world == 1) return;
+        const unsigned long long t0 = gtimer();
+        const int nrem = d.n3 - d.nown;
+        const long long total = (long long)d.r * nrem;
+        int bad = 0;
+        for (long long e = (long long)blockIdx.x * NT + tid; e < total; e += (long long)d.G * NT) {
+            const int jj = (int)(e / nrem), idx = (int)(e - (long long)jj * nrem);
+            const int row = idx < d.row0 ? idx : idx + d.nown;
+            const size_t off = (size_t)jj * d.ldq + row;
+            double v;
+            unsigned spins = 0;
+#pragma unroll 1
+            while (!ld_tagged(d.XtLL + off, xtag, v)) if (!spin_ok(spins, t0)) { bad = 1; break; }
+            if (bad) break;
+            d.Xt[off] = v;
+        }
+        if (__syncthreads_or(bad)) aborted = true;            // the next barrier fails on every CTA of every rank (abort flag raised)
+    }
+    // publish a freshly built operand to every consumer: world == 1 -> the grid barrier; else unpack + local barrier
+    __device__ __forceinline__ bool operand_sync() {
+        if (d.world == 1) return grid_sync();
+        unpack_operand();
+        return local_sync();
     }
     // the sum (and CTA 0's flag) gathered by the last grid_sync(); identical bits in every CTA
     __device__ __forceinline__ double collect(double* flag_out = nullptr) {
@@ -390,8 +497,8 @@ __device__ __forceinline__ void st3(double* A, int i, int r, int j, bool act, co
         p[0] = x[0]; p[r] = x[1]; p[2 * r] = x[2];
     }
 }
-// operand store (j-major, padded ld): the local copy, then every peer's copy (multi-GPU: this IS the all-gather of the
-// Q.Y operand — each CTA pushes the rows of its own cameras over NVLink; the next barrier publishes them)
+// operand store (j-major, padded ld): plain into the local copy; multi-GPU: tagged into every peer's staging copy (this IS
+// the all-gather of the Q.Y operand — each CTA pushes the rows of its own cameras over NVLink, the consumers poll the tags)
 template <class C>
 __device__ __forceinline__ void st_operand(const C& c, int i, bool act, const double (&x)[3]) {
     if (act) {
@@ -402,8 +509,8 @@ __device__ __forceinline__ void st_operand(const C& c, int i, bool act, const do
 #pragma unroll 1
             for (int w = 0; w < c.d.world; ++w) {
                 if (w == c.d.rank) continue;
-                double* q = c.d.Xt_peer[w] + off;
-                q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
+                ulonglong2* q = c.d.XtLL_peer[w] + off;
+                C::st_tagged(q, x[0], c.xtag); C::st_tagged(q + 1, x[1], c.xtag); C::st_tagged(q + 2, x[2], c.xtag);
             }
         }
     }

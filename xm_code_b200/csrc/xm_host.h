@@ -35,13 +35,13 @@ struct xm_handle {
     // operator rows held by this handle: cameras [cam0, cam1) (all of them unless a communicator is attached)
     int cam0 = 0, cam1 = 0;
     // multi-GPU communicator (xm_comm_*): one peer-mapped arena per rank with an identical layout everywhere
-    //   [bar 256][abort 256][partials][ll: barrier inbox][Xt: max_r * ldq][outR: n3 * max_r][outS: N]
+    //   [bar 256][abort 256][partials][ll: barrier inbox][slots: tagged partial sums][Xt: max_r * ldq][XtLL: tagged operand staging][outR][outS]
     int world = 1, rank = 0, comm_G = 0, comm_N = 0, comm_maxr = 0;
     bool comm_connected = false, comm_broken = false;
     char* arena = nullptr; size_t arena_bytes = 0;
     char* peer_arena[xm::kMaxWorld] = {};
     bool peer_ipc[xm::kMaxWorld] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
-    size_t off_bar = 0, off_abort = 0, off_partials = 0, off_ll = 0, off_xt = 0, off_outR = 0, off_outS = 0;
+    size_t off_bar = 0, off_abort = 0, off_partials = 0, off_ll = 0, off_slots = 0, off_xt = 0, off_xtll = 0, off_outR = 0, off_outS = 0;
 };
 
 #define XM_CUDA(h, call)                                                                           \

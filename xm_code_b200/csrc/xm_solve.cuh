@@ -52,6 +52,7 @@ __device__ __forceinline__ void phase_store_point(Ctx<RP, NT>& c, const double* 
 template <int RP, int NT>
 __device__ __forceinline__ void phase_operand_sR(Ctx<RP, NT>& c, const double* Y, const double* s) {
     const Dev& d = c.d;
+    c.begin_push();
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -67,6 +68,7 @@ __device__ __forceinline__ void phase_operand_sR(Ctx<RP, NT>& c, const double* Y
 template <int RP, int NT>
 __device__ __forceinline__ void phase_ls_trial(Ctx<RP, NT>& c, double alpha) {
     const Dev& d = c.d;
+    c.begin_push();
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -92,6 +94,7 @@ __device__ __forceinline__ double phase_grad(Ctx<RP, NT>& c, bool build_operand)
     const Dev& d = c.d;
     const int r = d.r, W = c.W;
     double part = 0.0;
+    if (build_operand) c.begin_push();
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -178,6 +181,7 @@ template <int RP, int NT>
 __device__ __forceinline__ void phase_dir(Ctx<RP, NT>& c, double beta) {
     const Dev& d = c.d;
     const int r = d.r;
+    c.begin_push();
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -203,6 +207,7 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
     const Dev& d = c.d;
     const int r = d.r;
     double part = 0.0;
+    c.begin_push();
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -233,6 +238,8 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
 }
 
 #define XM_GSYNC(c) do { if (!(c).grid_sync()) goto xm_abort; } while (0)
+// after a phase that built the Q.Y operand and is not followed by a reduction: publish the operand to its consumers
+#define XM_OSYNC(c) do { if (!(c).operand_sync()) goto xm_abort; } while (0)
 
 // ================================================================================================ the solver
 template <int RP, int NT, int PATH>
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
 
     phase_load_point(c, d.R0, d.s0);
     phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
-    XM_GSYNC(c);
+    XM_OSYNC(c);
     {   // f0 = objc(sR,s) and D = 2 Q sR at the start point (:362 / :422)
         ObjArgs oa{c.R(c.iY), c.S(c.iS), c.R(c.iD)};
         double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX);
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
         for (;;) {
             if (!first) alpha = alpha / 2;                                   // :378
             phase_ls_trial(c, alpha);
-            XM_GSYNC(c);
+            XM_OSYNC(c);
             ObjArgs oa{c.R(c.iYn), c.S(c.iS), c.R(c.iDn)};
             double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX);
             c.publish(part); XM_GSYNC(c); fnew = c.collect(); nqy++;
@@ -298,6 +305,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
         double tflag = 0.0;
         if (c.gc == 0 && c.tid == 0) tflag = ((double)((gtimer() - t_loop0) / 1000000000ull) > d.max_time) ? 1.0 : 0.0;   // :538-543 (one clock decides for all ranks)
         const double part = phase_grad(c, true);
+        c.unpack_operand();                      // multi-GPU: the peers' operand rows, before the reduction barrier publishes them
         c.publish(part, tflag); XM_GSYNC(c);
         double timeflag = 0.0;
         double rdotr = c.collect(&timeflag);
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
             c.tr(7);
             phase_dir(c, beta);
             c.tr(8);
-            XM_GSYNC(c);
+            XM_OSYNC(c);
             c.tr(9);
             const double nvv = vdotv + 2 * alpha * vdotp + alpha * alpha * pdotp;   // :642-644
             const double nvp = beta * (vdotp + alpha * pdotp);
@@ -355,6 +363,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
         totalite += i_inner + 1;                                                    // :666
 
         const double pm = phase_model_retract(c, c.R(V_V), c.S(S_VS), 1.0, true);
+        c.unpack_operand();
         c.publish(pm); XM_GSYNC(c);
         const double loss_qu = c.collect();
         if (loss_qu >= 0) { exit_code = 4; break; }                                 // :669-672
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
             trstatus = 3;                                                           // loss[k+1] = bestloss
             if (d_stale) {          // the reference recomputes everything from the restored (fresh) sR next iteration
                 phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
-                XM_GSYNC(c);
+                XM_OSYNC(c);
                 ObjArgs oa{c.R(c.iY), c.S(c.iS), c.R(c.iD)};
                 (void)qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX); nqy++;
                 XM_GSYNC(c);        // nobody may rewrite the operand while another CTA is still sweeping it
@@ -398,7 +407,7 @@ xm_finish:
     phase_store_point(c, c.R(c.iY), c.S(c.iS));
     // multi-GPU: the result rows were pushed into every rank's output copy; nobody's host may read its copy (or launch the
     // next solve, which rewrites the peers' operand) before all of them have landed
-    if (d.world > 1) { if (!c.grid_sync()) goto xm_abort; }
+    if (d.world > 1) { if (!c.grid_sync(true)) goto xm_abort; }
     c.save_epoch();
     if (lead) {
         DevStats& S = *d.stats;
@@ -438,6 +447,15 @@ __device__ __forceinline__ bool ops_body(Ctx<RP, NT>& c, const Dev& d, const QMa
     if (opcode == 5) {                 // grid-barrier micro-benchmark: |op_repeat| barriers back to back
         const int nrep = d.op_repeat < 0 ? -d.op_repeat : d.op_repeat;
         for (int rep = 0; rep < nrep; ++rep) { XM_GSYNC(c); }
+        if (c.tid == 0 && blockIdx.x == 0) for (int q = 0; q < 5; ++q) d.stats->dbg[q] = c.bseg[q];          // leader's segments
+        if (c.tid == 0 && blockIdx.x == 1) { d.stats->dbg[5] = c.bseg[0]; d.stats->dbg[6] = c.bseg[3]; d.stats->dbg[7] = c.bseg[4]; }
+        if (d.op_repeat < 0) {            // negative: as many operand exchanges (push + unpack + local barrier) on top, timed by the caller
+            for (int rep = 0; rep < nrep; ++rep) {
+                c.begin_push();
+                XM_FOR_OWN_CAMERAS(c, i, valid) { const double x[3] = {1.0 * rep, 2.0, 3.0}; st_operand(c, i, c.act && valid, x); }
+                XM_OSYNC(c);
+            }
+        }
         return true;
     }
     phase_load_point(c, d.R0, d.s0);
@@ -457,7 +475,7 @@ __device__ __forceinline__ bool ops_body(Ctx<RP, NT>& c, const Dev& d, const QMa
         return true;
     }
     phase_operand_sR(c, c.R(c.iY), c.S(c.iS));
-    XM_GSYNC(c);
+    XM_OSYNC(c);
     {
         ObjArgs oa{c.R(c.iY), c.S(c.iS), c.R(c.iD)};
         double part = qy_phase<RP, NT, MODE_OBJ, PATH>(c, oa, mapsQ.m, &mapX, opcode == 3);
@@ -476,6 +494,7 @@ __device__ __forceinline__ bool ops_body(Ctx<RP, NT>& c, const Dev& d, const QMa
         }
     }
     // opcode 3: overwrite P / ps with the caller's direction, build the operand, one Hessian-vector product
+    c.begin_push();
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -492,7 +511,7 @@ __device__ __forceinline__ bool ops_body(Ctx<RP, NT>& c, const Dev& d, const QMa
         double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
         st_operand(c, i, act, x);
     }
-    XM_GSYNC(c);
+    XM_OSYNC(c);
     {
         ObjArgs oa{nullptr, nullptr, nullptr};
         (void)qy_phase<RP, NT, MODE_HESS, PATH>(c, oa, mapsQ.m, &mapX, false);
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ D
     ring_init(c, dyn_smem);
     bool ok = ops_body<RP, NT, PATH>(c, d, mapsQ, mapX, opcode);
     // multi-GPU: results were pushed to every rank and the peers' operand copies may still be in use — leave together
-    if (ok && d.world > 1) ok = c.grid_sync();
+    if (ok && d.world > 1) ok = c.grid_sync(true);
     if (ok) c.save_epoch();
     else ring_drain(c);
 }
