@@ -120,6 +120,21 @@ def test_qy_dense_matches_oracle(team_factory, N, r, opts):
         assert rel(got, -Q @ X) < TOL
 
 
+def test_bsr_solve_matches_oracle_both_protocols(team_factory, monkeypatch):
+    from xm_code_b200 import problems
+    N = 300
+    rowptr, col, vals = problems.erdos_renyi_bsr(N, avg_degree=8, seed=2)
+    Q = problems.bsr_to_dense(rowptr, col, vals)
+    ref = xo.trust_region(Q, xo.identity_init(N, 4), np.ones(N), 0.0, 1e-7)
+    for push in ("0", "1"):
+        monkeypatch.setenv("XM_TUNE_PUSH", push)
+        t = team_factory(N, 4)
+        t.call("set_q_bsr", rowptr, col, vals, 3)
+        for got in t.call("trust_region", xo.from_blocks(xo.identity_init(N, 4)), np.ones(N), 0.0, 1e-7):
+            assert abs(got.primal - ref.primal) <= 1e-8 * abs(ref.primal)
+            np.testing.assert_allclose(got.s, ref.s, atol=1e-6, rtol=0)
+
+
 def test_qy_bsr_matches_dense(team_factory):
     from xm_code_b200 import problems
     rowptr, col, vals = problems.erdos_renyi_bsr(400, avg_degree=12, seed=4)
@@ -182,9 +197,11 @@ def test_solve_simple1_matches_oracle_on_every_rank(team_factory, simple1_q):
         assert got.primal == res[0].primal
 
 
+@pytest.mark.parametrize("push", ["0", "1"])          # operand exchange protocol: tagged words / plain stores + .sys-fenced barrier
 @pytest.mark.parametrize("opts", [{}, dict(vec_in_global=True), dict(qy_variant=1)])
-def test_solve_synthetic_with_regulariser(team_factory, opts):
+def test_solve_synthetic_with_regulariser(team_factory, opts, push, monkeypatch):
     from xm_code_b200 import problems
+    monkeypatch.setenv("XM_TUNE_PUSH", push)
     N = 400
     Q, _ = problems.synthetic_dense_q(N, seed=5)
     ref = xo.trust_region(Q, xo.identity_init(N, 3), np.ones(N), 0.05, 1e-8)

@@ -436,6 +436,10 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         d.ll = (unsigned long long*)(h->arena + h->off_ll);
         d.slots_ll = (ulonglong2*)(h->arena + h->off_slots); d.XtLL = (ulonglong2*)(h->arena + h->off_xtll);
         d.nown = 3 * (h->cam1 - h->cam0);
+        // protocol switch (like NCCL's LL vs Simple): tagged words double the bytes but need no fence; above ~2 MB per rank and
+        // exchange the NVLink time of the extra bytes outweighs the 3.5 us fence
+        d.push_plain = ((size_t)d.nown * r * sizeof(double) * (h->world - 1) > (size_t)(2 << 20)) ? 1 : 0;
+        if (const char* e = getenv("XM_TUNE_PUSH")) d.push_plain = atoi(e) ? 1 : 0;                 // A/B hook
         for (int w = 0; w < h->world; ++w) {
             d.Xt_peer[w] = (double*)(h->peer_arena[w] + h->off_xt); d.ll_peer[w] = (unsigned long long*)(h->peer_arena[w] + h->off_ll);
             d.XtLL_peer[w] = (ulonglong2*)(h->peer_arena[w] + h->off_xtll);

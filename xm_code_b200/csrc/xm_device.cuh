@@ -62,6 +62,9 @@ struct Dev {
     ulonglong2* XtLL;                          // this GPU's staging copy of the operand rows owned by peers (tagged, 16 B per double)
     ulonglong2* XtLL_peer[kMaxWorld];
     int nown;                                  // rows of the operand this rank owns: 3 * (cam1 - cam0), starting at row0
+    int push_plain;                            // operand exchange protocol: 0 = tagged words polled by the consumers (latency-bound
+                                               // sizes: no fence, twice the bytes), 1 = plain stores into the peers' Xt published by a
+                                               // .sys-fenced cross-GPU barrier (bandwidth-bound sizes: +3.5 us fence, half the bytes)
     int* abort_peer[kMaxWorld];
     double* outR_peer[kMaxWorld];              // results in the wire layout (3N x r col-major / length N): every CTA stores its
     double* outS_peer[kMaxWorld];              // own cameras into every rank's copy
@@ -453,7 +456,7 @@ struct Ctx {
     // (operand_sync(): a local one; or the cross-GPU reduction that was due anyway) publishes them to the local consumers.
     __device__ __forceinline__ void begin_push() { xtag += 1; }
     __device__ __forceinline__ void unpack_operand() {
-        if (d.world == 1) return;
+        if (d.world == 1 || d.push_plain) return;
         const unsigned long long t0 = gtimer();
         const int nrem = d.n3 - d.nown;
         const long long total = (long long)d.r * nrem;
@@ -474,6 +477,7 @@ struct Ctx {
     // publish a freshly built operand to every consumer: world == 1 -> the grid barrier; else unpack + local barrier
     __device__ __forceinline__ bool operand_sync() {
         if (d.world == 1) return grid_sync();
+        if (d.push_plain) return grid_sync(true);             // plain rows in the peers' Xt: the .sys-fenced barrier publishes them
         unpack_operand();
         return local_sync();
     }
@@ -509,8 +513,13 @@ __device__ __forceinline__ void st_operand(const C& c, int i, bool act, const do
 #pragma unroll 1
             for (int w = 0; w < c.d.world; ++w) {
                 if (w == c.d.rank) continue;
-                ulonglong2* q = c.d.XtLL_peer[w] + off;
-                C::st_tagged(q, x[0], c.xtag); C::st_tagged(q + 1, x[1], c.xtag); C::st_tagged(q + 2, x[2], c.xtag);
+                if (c.d.push_plain) {
+                    double* q = c.d.Xt_peer[w] + off;
+                    q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
+                } else {
+                    ulonglong2* q = c.d.XtLL_peer[w] + off;
+                    C::st_tagged(q, x[0], c.xtag); C::st_tagged(q + 1, x[1], c.xtag); C::st_tagged(q + 2, x[2], c.xtag);
+                }
             }
         }
     }

@@ -240,6 +240,8 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
 #define XM_GSYNC(c) do { if (!(c).grid_sync()) goto xm_abort; } while (0)
 // after a phase that built the Q.Y operand and is not followed by a reduction: publish the operand to its consumers
 #define XM_OSYNC(c) do { if (!(c).operand_sync()) goto xm_abort; } while (0)
+// reduction barrier right after a phase that also built the operand (plain-push protocol: it must publish the remote rows)
+#define XM_GSYNC_PUSHED(c) do { if (!(c).grid_sync((c).d.world > 1 && (c).d.push_plain != 0)) goto xm_abort; } while (0)
 
 // ================================================================================================ the solver
 template <int RP, int NT, int PATH>
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
         if (c.gc == 0 && c.tid == 0) tflag = ((double)((gtimer() - t_loop0) / 1000000000ull) > d.max_time) ? 1.0 : 0.0;   // :538-543 (one clock decides for all ranks)
         const double part = phase_grad(c, true);
         c.unpack_operand();                      // multi-GPU: the peers' operand rows, before the reduction barrier publishes them
-        c.publish(part, tflag); XM_GSYNC(c);
+        c.publish(part, tflag); XM_GSYNC_PUSHED(c);
         double timeflag = 0.0;
         double rdotr = c.collect(&timeflag);
         gradnorm = sqrt(rdotr);
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
 
         const double pm = phase_model_retract(c, c.R(V_V), c.S(S_VS), 1.0, true);
         c.unpack_operand();
-        c.publish(pm); XM_GSYNC(c);
+        c.publish(pm); XM_GSYNC_PUSHED(c);
         const double loss_qu = c.collect();
         if (loss_qu >= 0) { exit_code = 4; break; }                                 // :669-672
         {
