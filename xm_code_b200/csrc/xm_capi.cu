@@ -31,6 +31,15 @@ __global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld,
     }
 }
 
+// wire layout (3N x r column-major) -> camera-major operand dst[row * r + j] (block-CSR path)
+__global__ void xm_operand_cam_major_kernel(const double* __restrict__ src, int n3, int r, double* __restrict__ dst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)n3 * r) {
+        const int j = (int)(t / n3), row = (int)(t - (long long)j * n3);      // coalesced reads
+        dst[(size_t)row * r + j] = src[t];
+    }
+}
+
 }  // namespace xm
 
 static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -412,9 +421,9 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         if (cudaMalloc(&h->ws, total) != cudaSuccess) { cudaGetLastError(); h->err = "workspace cudaMalloc failed"; return XM_ENOMEM; }
         h->ws_cap = total; fresh = true;
     }
-    if (fresh || h->ws_r != r || h->ws_N != (int)N || h->ws_G != p.GT || h->ws_ldq != (int)ldq) {
+    if (fresh || h->ws_r != r || h->ws_N != (int)N || h->ws_G != p.GT || h->ws_ldq != (int)ldq || h->ws_bsr != (int)h->is_bsr) {
         XM_CUDA(h, cudaMemsetAsync(h->ws, 0, total, h->stream));
-        h->ws_r = r; h->ws_N = (int)N; h->ws_G = p.GT; h->ws_ldq = (int)ldq;
+        h->ws_r = r; h->ws_N = (int)N; h->ws_G = p.GT; h->ws_ldq = (int)ldq; h->ws_bsr = (int)h->is_bsr;
     }
     char* q = h->ws;
     Dev& d = h->dev;
@@ -425,6 +434,7 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.Xt = (double*)q; q += align_up((size_t)r * ldq * sizeof(double), 256);
     d.partials = (double*)q;
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
+    d.x_cam_major = h->is_bsr ? 1 : 0;
     d.Q = h->is_bsr ? nullptr : h->Qp;
     d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim;
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;
@@ -550,9 +560,21 @@ static int qy_common(xm_handle* h, int r, double alpha, const double* X, double*
     if (!X || !out) return XM_EINVAL;
     Dev d = h->dev;
     const cudaMemcpyKind kin = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    // the wire layout (3N x r column-major) IS the operand layout up to the padded leading dimension
-    XM_CUDA(h, cudaMemcpy2DAsync(d.Xt, (size_t)d.ldq * sizeof(double), X, (size_t)d.n3 * sizeof(double),
-                                 (size_t)d.n3 * sizeof(double), r, kin, h->stream));
+    if (d.x_cam_major) {      // block-CSR: camera-major operand
+        const double* src = X;
+        if (!dev_ptrs) {
+            XM_CUDA(h, cudaMemcpyAsync(h->io_P, X, (size_t)d.n3 * r * sizeof(double), kin, h->stream));
+            src = h->io_P;
+        }
+        const long long tot = (long long)d.n3 * r;
+        xm_operand_cam_major_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(src, d.n3, r, d.Xt);
+        XM_CUDA(h, cudaGetLastError());
+        h->launches++;
+    } else {
+        // the wire layout (3N x r column-major) IS the operand layout up to the padded leading dimension
+        XM_CUDA(h, cudaMemcpy2DAsync(d.Xt, (size_t)d.ldq * sizeof(double), X, (size_t)d.n3 * sizeof(double),
+                                     (size_t)d.n3 * sizeof(double), r, kin, h->stream));
+    }
     d.qy_alpha = alpha;
     const OutBind ob = bind_out(h, d, dev_ptrs ? out : h->io_Rout, h->io_sout);
     XM_CUDA(h, launch_ops(h, d, 0, p, h->stream));

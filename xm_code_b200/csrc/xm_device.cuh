@@ -86,6 +86,8 @@ struct Dev {
     int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
     int profile;               // fine-grained phase timers on (costs a few percent)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
+    int x_cam_major;           // operand layout: 0 = j-major Xt[j*ldq + row] (dense paths, TMA boxes), 1 = camera-major Xt[row*r + j]
+                               // (block-CSR: the 3r doubles a block needs are contiguous)
     double *partials;          // kPartialBufs * (G + 1) * kPartialStride: the reduction slots of THIS GPU's CTAs
     unsigned long long* bar;   // barrier counter of THIS GPU's CTAs, monotone
     int* abort_flag;
@@ -113,6 +115,11 @@ __device__ __forceinline__ double2 ldg_stream_v2(const double* p) {
     double2 v;
     asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
+}
+
+// one row of a padded 4x4 block: 32 bytes in one request (LDG.E.256)
+__device__ __forceinline__ void ldg_stream_v4(const double* p, double (&v)[4]) {
+    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
@@ -462,9 +469,11 @@ struct Ctx {
         const long long total = (long long)d.r * nrem;
         int bad = 0;
         for (long long e = (long long)blockIdx.x * NT + tid; e < total; e += (long long)d.G * NT) {
-            const int jj = (int)(e / nrem), idx = (int)(e - (long long)jj * nrem);
+            int jj, idx;                                      // consecutive threads walk the layout's fast axis
+            if (d.x_cam_major) { idx = (int)(e / d.r); jj = (int)(e - (long long)idx * d.r); }
+            else               { jj = (int)(e / nrem); idx = (int)(e - (long long)jj * nrem); }
             const int row = idx < d.row0 ? idx : idx + d.nown;
-            const size_t off = (size_t)jj * d.ldq + row;
+            const size_t off = d.x_cam_major ? (size_t)row * d.r + jj : (size_t)jj * d.ldq + row;
             double v;
             unsigned spins = 0;
 #pragma unroll 1
@@ -506,19 +515,20 @@ __device__ __forceinline__ void st3(double* A, int i, int r, int j, bool act, co
 template <class C>
 __device__ __forceinline__ void st_operand(const C& c, int i, bool act, const double (&x)[3]) {
     if (act) {
-        const size_t off = (size_t)c.j * c.d.ldq + 3 * i;
+        const size_t off = c.d.x_cam_major ? (size_t)(3 * i) * c.d.r + c.j : (size_t)c.j * c.d.ldq + 3 * i;
+        const size_t rs = c.d.x_cam_major ? (size_t)c.d.r : 1;             // distance between the camera's three rows
         double* p = c.d.Xt + off;
-        p[0] = x[0]; p[1] = x[1]; p[2] = x[2];
+        p[0] = x[0]; p[rs] = x[1]; p[2 * rs] = x[2];
         if (c.d.world > 1) {
 #pragma unroll 1
             for (int w = 0; w < c.d.world; ++w) {
                 if (w == c.d.rank) continue;
                 if (c.d.push_plain) {
                     double* q = c.d.Xt_peer[w] + off;
-                    q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
+                    q[0] = x[0]; q[rs] = x[1]; q[2 * rs] = x[2];
                 } else {
                     ulonglong2* q = c.d.XtLL_peer[w] + off;
-                    C::st_tagged(q, x[0], c.xtag); C::st_tagged(q + 1, x[1], c.xtag); C::st_tagged(q + 2, x[2], c.xtag);
+                    C::st_tagged(q, x[0], c.xtag); C::st_tagged(q + rs, x[1], c.xtag); C::st_tagged(q + 2 * rs, x[2], c.xtag);
                 }
             }
         }
@@ -593,38 +603,43 @@ __device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, 
     }
 }
 
-// Block-CSR: one warp per block row (camera); lanes stride over the row's blocks.  Blocks are stored 4x4 row-major
-// (128 B, one coalesced line per block); operand rows gathered through L1/L2.  bdim==3: rows/cols 3 unused (zero).
-template <int RP>
-__device__ __forceinline__ void qy_sweep_bsr(const Dev& d, int cam, int part, int nparts, int lane, double (&acc)[3][RP]) {
+// Block-CSR: one warp per block row (camera).  The warp's sub-warps (W lanes each, the same sub-warp geometry as every
+// per-camera phase) deal the row's blocks out round-robin; lane j of a sub-warp holds column j of the 3 x r result.  Per
+// block a lane issues three 32-byte broadcast loads (the block's rows: blocks are stored 4x4 row-major = one 128-byte line,
+// read once from HBM, never allocated in L1), and three operand loads that are contiguous across the sub-warp because the
+// operand is CAMERA-MAJOR here (Xt[(3c+a) r + j]: the 3r doubles of camera c are adjacent) — 11 sectors per block at r = 10
+// against 36 with the j-major layout the dense paths use (ncu: profiles/r01_bsr_qy.md).  The column index is fetched one
+// block ahead so its latency is off the operand-gather chain.  bdim == 3: row / column 3 of a block are zero padding.
+__device__ __forceinline__ void qy_sweep_bsr(const Dev& d, int cam, int part, int nparts, int W, int cpw, int sw, int j, bool act,
+                                             double (&E)[3]) {
     const int r = d.r;
-    const size_t ldq = (size_t)d.ldq;
     const int b0 = d.bsr_rowptr[cam - d.cam0], b1 = d.bsr_rowptr[cam - d.cam0 + 1];   // local block rows [cam0, cam1)
-    const double* xt = d.Xt;
-    for (int b = b0 + part * 32 + lane; b < b1; b += 32 * nparts) {
-        const int c = d.bsr_col[b];
+    const double* xc = d.Xt;
+    const int stride = cpw * nparts;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    int b = b0 + part * cpw + sw;
+    int c = (b < b1) ? __ldg(d.bsr_col + b) : 0;
+#pragma unroll 2
+    for (; b < b1; b += stride) {
+        const int bn = b + stride;
+        const int cn = (bn < b1) ? __ldg(d.bsr_col + bn) : 0;
         const double* blk = d.bsr_val + (size_t)b * 16;
-        double q[3][3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const double2 u = ldg_stream_v2(blk + 4 * a);
-            const double2 w = ldg_stream_v2(blk + 4 * a + 2);
-            q[a][0] = u.x; q[a][1] = u.y; q[a][2] = w.x;
+        double q0[4], q1[4], q2[4];
+        ldg_stream_v4(blk, q0); ldg_stream_v4(blk + 4, q1); ldg_stream_v4(blk + 8, q2);
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+        if (act) {
+            const double* xp = xc + (size_t)(3 * c) * r + j;
+            x0 = xp[0]; x1 = xp[r]; x2 = xp[2 * r];
         }
-#pragma unroll
-        for (int jj = 0; jj < RP; ++jj) {
-            if (jj < r) {
-                const double* xp = xt + (size_t)jj * ldq + 3 * c;
-                const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    acc[a][jj] = fma(q[a][0], x0, acc[a][jj]);
-                    acc[a][jj] = fma(q[a][1], x1, acc[a][jj]);
-                    acc[a][jj] = fma(q[a][2], x2, acc[a][jj]);
-                }
-            }
-        }
+        e0 = fma(q0[0], x0, e0); e0 = fma(q0[1], x1, e0); e0 = fma(q0[2], x2, e0);
+        e1 = fma(q1[0], x0, e1); e1 = fma(q1[1], x1, e1); e1 = fma(q1[2], x2, e1);
+        e2 = fma(q2[0], x0, e2); e2 = fma(q2[1], x1, e2); e2 = fma(q2[2], x2, e2);
+        c = cn;
     }
+    for (int off = W; off < 32; off <<= 1) {                 // fixed-order butterfly over the warp's sub-warps
+        e0 += shfl_xor_d(e0, off); e1 += shfl_xor_d(e1, off); e2 += shfl_xor_d(e2, off);
+    }
+    E[0] = e0; E[1] = e1; E[2] = e2;
 }
 
 // ------------------------------------------------------------------------------------------------ per-camera epilogues
@@ -723,8 +738,8 @@ __device__ __forceinline__ void warp_reduce_to_red(Ctx<RP, NT>& c, double (&acc)
         }
 }
 
-// ---- direct-load path (dense without TMA, and block-CSR): all warps of the CTA stream
-template <int RP, int NT, int MODE>
+// ---- direct-load paths: dense without TMA (BSR = false) and block-CSR (BSR = true): all warps of the CTA stream
+template <int RP, int NT, int MODE, bool BSR>
 __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs& oa) {
     const Dev& d = c.d;
     const int KS = d.KS, CB = d.CB;
@@ -735,16 +750,21 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs&
     const int kend = (int)(((long long)(ks + 1) * steps) / KS) * 64;
     for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
         const int cam = b0 + cslot;
-        double acc[3][RP];
+        if (BSR) {
+            double E[3] = {0.0, 0.0, 0.0};
+            if (cam < c.cam_hi) qy_sweep_bsr(d, cam, ks, KS, c.W, c.cpw, c.sw, c.j, c.act, E);
+            if (c.lane < c.W && c.j < RP) {                 // the warp's totals, column j: same slots warp_reduce_to_red fills
+                c.red[(c.warp * 3 + 0) * RP + c.j] = E[0]; c.red[(c.warp * 3 + 1) * RP + c.j] = E[1]; c.red[(c.warp * 3 + 2) * RP + c.j] = E[2];
+            }
+        } else {
+            double acc[3][RP];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
-        if (cam < c.cam_hi) {
-            if (d.Q) qy_sweep_dense<RP>(d, cam, kbeg, kend, c.lane, acc);
-            else     qy_sweep_bsr<RP>(d, cam, ks, KS, c.lane, acc);
+                for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
+            if (cam < c.cam_hi) qy_sweep_dense<RP>(d, cam, kbeg, kend, c.lane, acc);
+            warp_reduce_to_red<RP, NT>(c, acc);
         }
-        warp_reduce_to_red<RP, NT>(c, acc);
         __syncthreads();
         part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, min(CB, c.cam_hi - b0), KS, CB);
         __syncthreads();
@@ -888,7 +908,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
     return part;
 }
 
-// PATH: 0 = dense through the TMA ring, 1 = direct loads (dense qy_variant=1, and block-CSR).  A kernel is compiled for one
+// PATH: 0 = dense through the TMA ring, 1 = dense by direct loads (qy_variant=1), 2 = block-CSR.  A kernel is compiled for one
 // path only, so the register budget of the persistent kernel is not set by the path it does not run.
 template <int RP, int NT, int MODE, int PATH>
 __device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa, const CUtensorMap* mapQ, const CUtensorMap* mapX,
@@ -896,8 +916,9 @@ __device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa, co
     unsigned long long t0 = 0;
     if (blockIdx.x == 0 && c.tid == 0) t0 = gtimer();
     double part;
-    if (PATH == 0) part = qy_phase_tma<RP, NT, MODE>(c, oa, mapQ, mapX, prefetch_next);
-    else           part = qy_phase_direct<RP, NT, MODE>(c, oa);
+    if (PATH == 0)      part = qy_phase_tma<RP, NT, MODE>(c, oa, mapQ, mapX, prefetch_next);
+    else if (PATH == 1) part = qy_phase_direct<RP, NT, MODE, false>(c, oa);
+    else                part = qy_phase_direct<RP, NT, MODE, true>(c, oa);
     if (blockIdx.x == 0 && c.tid == 0) c.t_qy += gtimer() - t0;
     return part;
 }

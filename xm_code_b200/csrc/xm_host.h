@@ -16,7 +16,7 @@ struct xm_handle {
     double* Qstage = nullptr; size_t Qstage_cap = 0;   // staging for the user's column-major matrix
     int* bsr_rowptr = nullptr; int* bsr_col = nullptr; double* bsr_val = nullptr; int bsr_bdim = 0; bool is_bsr = false;
     // workspace (one allocation, carved per (N, r))
-    char* ws = nullptr; size_t ws_cap = 0; int ws_r = -1, ws_N = -1, ws_G = -1, ws_ldq = -1;
+    char* ws = nullptr; size_t ws_cap = 0; int ws_r = -1, ws_N = -1, ws_G = -1, ws_ldq = -1, ws_bsr = -1;
     xm::Dev dev{};                                         // pointer template, filled by carve()
     // small persistent device objects
     xm::DevStats* d_stats = nullptr; xm::LogRec* d_log = nullptr; int* d_abort = nullptr;

@@ -12,8 +12,9 @@ using namespace xm;
 template <int RP, int NT>
 static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     const void* fn;
-    if (kind == 0) fn = d.use_tma ? (const void*)xm_solve_kernel<RP, NT, 0> : (const void*)xm_solve_kernel<RP, NT, 1>;
-    else           fn = d.use_tma ? (const void*)xm_ops_kernel<RP, NT, 0> : (const void*)xm_ops_kernel<RP, NT, 1>;
+    // PATH: 0 = dense through the TMA ring, 1 = dense by direct loads, 2 = block-CSR
+    if (kind == 0) fn = d.use_tma ? (const void*)xm_solve_kernel<RP, NT, 0> : d.Q ? (const void*)xm_solve_kernel<RP, NT, 1> : (const void*)xm_solve_kernel<RP, NT, 2>;
+    else           fn = d.use_tma ? (const void*)xm_ops_kernel<RP, NT, 0> : d.Q ? (const void*)xm_ops_kernel<RP, NT, 1> : (const void*)xm_ops_kernel<RP, NT, 2>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     if (kind == 0) {

@@ -18,8 +18,10 @@ import scipy.linalg as sla
 import scipy.sparse as sp
 
 
-def q_from_observations(n_cameras: int, n_landmarks: int, cam, lm, w, pt) -> np.ndarray:
-    """Dense 3N x 3N float64 Q from observations.  cam, lm: int arrays (nobs); w: (nobs,); pt: (nobs, 3)."""
+def q_from_observations(n_cameras: int, n_landmarks: int, cam, lm, w, pt, return_abar: bool = False):
+    """Dense 3N x 3N float64 Q from observations.  cam, lm: int arrays (nobs); w: (nobs,); pt: (nobs, 3).
+    return_abar: also return Abar ((N + M - 1) x 3N), the map (sR)^T -> [t_2..t_N; p_1..p_M] of the eliminated
+    translations / landmarks (the reference's Abar.bin, utils/creatematrix.py:308-311): Abar = -Lbar^{-1} Vbar^T."""
     N, M = int(n_cameras), int(n_landmarks)
     cam = np.asarray(cam, dtype=np.int64); lm = np.asarray(lm, dtype=np.int64)
     w = np.asarray(w, dtype=np.float64); pt = np.asarray(pt, dtype=np.float64)
@@ -55,7 +57,14 @@ def q_from_observations(n_cameras: int, n_landmarks: int, cam, lm, w, pt) -> np.
     for a in range(3):
         for b in range(3):
             Q[3 * idx + a, 3 * idx + b] += Q1[:, a, b]
-    return 0.5 * (Q + Q.T)
+    Q = 0.5 * (Q + Q.T)
+    if not return_abar:
+        return Q
+    # Lbar [a; b] = -Vbar^T with the landmark block eliminated:  Sc a = -Bb^T ,  b = Dl^{-1} (-Vl^T + Wbar^T a)
+    a_t = -sla.cho_solve(cho, Bb.T, check_finite=False)                  # (N-1) x 3N : translations t_2 .. t_N
+    Wb = W[1:, :]
+    b_p = Dl_inv @ (-Vl.T.toarray() + Wb.T @ a_t)                        # M x 3N     : landmarks
+    return Q, np.vstack([a_t, b_p])
 
 
 def random_rotations(n: int, rng) -> np.ndarray:
