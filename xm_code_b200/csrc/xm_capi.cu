@@ -389,6 +389,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.vec_smem = (h->opt.vec_in_global == 0 && p.vec_bytes <= 64 * 1024) ? 1 : 0;
     if (p.vec_smem) budget -= p.vec_bytes;
     p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
+    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * (kBsrChunk * 128 + 8);      // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
     if (p.use_tma) {
         p.nbmax = std::min(p.CB, cpc);
         p.stage_doubles = (3 * p.nbmax + p.RP) * p.KC;   // operand area sized for the padded rank (consumers read RP rows)
@@ -436,7 +437,7 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
     d.x_cam_major = h->is_bsr ? 1 : 0;
     d.Q = h->is_bsr ? nullptr : h->Qp;
-    d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim;
+    if (h->is_bsr) { d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim; }   // else null: dense
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;
     d.rank = h->rank; d.world = h->world; d.GT = p.GT; d.g0 = h->rank * p.G; d.cam0 = h->cam0; d.row0 = 3 * h->cam0;
     d.bar = h->d_bar; d.abort_flag = h->d_abort; d.epoch_store = h->d_bar + 16;

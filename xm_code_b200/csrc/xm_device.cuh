@@ -23,6 +23,7 @@ constexpr int kLogCap = 1002;
 constexpr int kPartialBufs = 4;
 constexpr int kKC = 192;            // TMA ring: columns per chunk (box inner dimension, <= 256); see profiles/r01_sweep_ring_*.txt
 constexpr int kPartialStride = 1;   // doubles per slot; GT slots for the CTA sums + 1 for global CTA 0's flag, x kPartialBufs rotating buffers
+constexpr int kBsrChunk = 32;       // block-CSR: blocks per staged chunk (32 x 128 B = one 4 KB bulk copy; one column index per lane)
 constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node that can share a solve (camera partition, peer-mapped exchange)
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
@@ -162,6 +163,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(col0), "r"(row0), "r"(smem_u32(bar)) : "memory");
 }
+// 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned), completion on an mbarrier.
+// L2 evict_first: the blocks of Q are read once per product and must not push the (heavily re-read) operand out of L2.
+__device__ __forceinline__ void tma_load_1d_stream(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // explicit shared-window load (the ring pointer is generic; a generic LD costs more than LDS).  volatile: stays ordered
 // after the volatile mbarrier wait and before the volatile arrive.
 __device__ __forceinline__ double2 lds_v2(unsigned saddr) {
@@ -219,6 +231,7 @@ struct Ctx {
     // TMA ring state (grid-uniform): running use counter (stage = g % ST, parity = (g / ST) & 1) and how many of the
     // next phase's uses already have their Q tiles in flight (cross-phase prefetch)
     double* ring; unsigned long long *fullQ, *fullX, *empty;
+    double* bsr_buf; unsigned long long* bsr_bar; unsigned bsr_phase;   // block-CSR: this warp's two staged chunks, their mbarriers, parity bits
     unsigned g_use; int prefetched;
     double* red;                // smem [NWARPS][3][RP]
     double* bsum;               // smem [NWARPS]
@@ -243,6 +256,7 @@ struct Ctx {
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
         ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
+        bsr_buf = nullptr; bsr_bar = nullptr; bsr_phase = 0;
     }
     // end of a launch: remember the epoch for the next one (every CTA has long read epoch_store by now: it sits behind at
     // least one barrier whenever the value changes)
@@ -603,43 +617,82 @@ __device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, 
     }
 }
 
-// Block-CSR: one warp per block row (camera).  The warp's sub-warps (W lanes each, the same sub-warp geometry as every
-// per-camera phase) deal the row's blocks out round-robin; lane j of a sub-warp holds column j of the 3 x r result.  Per
-// block a lane issues three 32-byte broadcast loads (the block's rows: blocks are stored 4x4 row-major = one 128-byte line,
-// read once from HBM, never allocated in L1), and three operand loads that are contiguous across the sub-warp because the
-// operand is CAMERA-MAJOR here (Xt[(3c+a) r + j]: the 3r doubles of camera c are adjacent) — 11 sectors per block at r = 10
-// against 36 with the j-major layout the dense paths use (ncu: profiles/r01_bsr_qy.md).  The column index is fetched one
-// block ahead so its latency is off the operand-gather chain.  bdim == 3: row / column 3 of a block are zero padding.
-__device__ __forceinline__ void qy_sweep_bsr(const Dev& d, int cam, int part, int nparts, int W, int cpw, int sw, int j, bool act,
-                                             double (&E)[3]) {
-    const int r = d.r;
-    const int b0 = d.bsr_rowptr[cam - d.cam0], b1 = d.bsr_rowptr[cam - d.cam0 + 1];   // local block rows [cam0, cam1)
+// Block-CSR Q.Y: one warp per block row (camera), blocks stored 4x4 row-major = one 128-byte line each (row / column 3 are
+// zero padding for bdim == 3), operand CAMERA-MAJOR (Xt[(3c+a) r + j]: the 3r doubles a block needs are adjacent).
+//
+//   * Q blocks: the warp stages its row through shared memory in chunks of kBsrChunk = 32 blocks — ONE 4 KB bulk copy (1-D TMA,
+//     cp.async.bulk, L2 evict_first) per chunk into one of the warp's two buffers, completion on the warp's own mbarrier;
+//     the next chunk (of this row, or the first of the warp's next row) is in flight while the current one is consumed, so
+//     ~64 KB of Q per SM are in flight without holding a register.  The 32 column indices of a chunk are one coalesced load
+//     (one per lane), handed out by shuffles.
+//   * operand gather: the warp's sub-warps (W lanes, the geometry of every per-camera phase) deal the chunk's blocks out
+//     round-robin; lane j of a sub-warp owns column j.  Four blocks per sub-warp are gathered at once (12 independent loads
+//     per lane, each contiguous across the sub-warp: 11 sectors per block at r = 10 against 36 with the j-major layout of
+//     the dense paths), then multiplied with the block read from shared memory (LDS broadcasts).
+//   * the 3 x r result of the row ends up as 3 registers per lane after a fixed-order butterfly over the sub-warps —
+//     the layout the per-camera epilogue wants.
+// History (profiles/r01_bsr_qy.md): v1 lane-per-block with j-major operand was L1TEX-bound (81 %, 371 M sectors); v2 (this
+// mapping, blocks through registers) and v3 (+ L2 prefetch of the next row) were latency-bound at 16 warps per SM.
+struct BsrCursor {           // the warp's position in its sequence of chunks: rows cam, cam + CB, ... ; chunks part, part + nparts, ...
+    int cam, q, rb0, rb1;
+    __device__ __forceinline__ bool valid() const { return cam >= 0; }
+    __device__ __forceinline__ int start() const { return rb0 + q * kBsrChunk; }
+    __device__ __forceinline__ int count() const { return min(kBsrChunk, rb1 - start()); }
+};
+__device__ __forceinline__ void bsr_seek(const Dev& d, BsrCursor& cu, int cam_hi, int part, int CB) {   // first non-empty chunk at or after (cam, q)
+    while (cu.cam < cam_hi) {
+        cu.rb0 = d.bsr_rowptr[cu.cam - d.cam0]; cu.rb1 = d.bsr_rowptr[cu.cam - d.cam0 + 1];
+        if (cu.rb0 + cu.q * kBsrChunk < cu.rb1) return;
+        cu.cam += CB; cu.q = part;
+    }
+    cu.cam = -1;
+}
+template <class C>
+__device__ __forceinline__ int bsr_issue(C& c, const BsrCursor& cu, int buf, unsigned long long policy) {   // returns this lane's column index
+    const Dev& d = c.d;
+    const int st = cu.start(), nb = cu.count();
+    __syncwarp();                                            // every lane is done with the buffer's previous chunk
+    if (c.lane == 0) {
+        mbar_expect_tx(&c.bsr_bar[buf], (unsigned)nb * 128u);
+        tma_load_1d_stream(c.bsr_buf + (size_t)buf * kBsrChunk * 16, d.bsr_val + (size_t)st * 16, (unsigned)nb * 128u, &c.bsr_bar[buf], policy);
+    }
+    return (c.lane < nb) ? __ldg(d.bsr_col + st + c.lane) : 0;
+}
+// consume one staged chunk: E += sum over the sub-warp's blocks of block * operand rows
+template <class C>
+__device__ __forceinline__ bool bsr_consume(C& c, int nb, int buf, int colreg, double (&E)[3]) {
+    const Dev& d = c.d;
+    constexpr int K = 4;
+    const int r = d.r, cpw = c.cpw;
+    if (!mbar_wait(&c.bsr_bar[buf], (c.bsr_phase >> buf) & 1u)) return false;
+    c.bsr_phase ^= 1u << buf;
+    const unsigned sbuf = smem_u32(c.bsr_buf + (size_t)buf * kBsrChunk * 16);
     const double* xc = d.Xt;
-    const int stride = cpw * nparts;
-    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
-    int b = b0 + part * cpw + sw;
-    int c = (b < b1) ? __ldg(d.bsr_col + b) : 0;
-#pragma unroll 2
-    for (; b < b1; b += stride) {
-        const int bn = b + stride;
-        const int cn = (bn < b1) ? __ldg(d.bsr_col + bn) : 0;
-        const double* blk = d.bsr_val + (size_t)b * 16;
-        double q0[4], q1[4], q2[4];
-        ldg_stream_v4(blk, q0); ldg_stream_v4(blk + 4, q1); ldg_stream_v4(blk + 8, q2);
-        double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-        if (act) {
-            const double* xp = xc + (size_t)(3 * c) * r + j;
-            x0 = xp[0]; x1 = xp[r]; x2 = xp[2 * r];
+    for (int g0 = 0; g0 < nb; g0 += K * cpw) {               // warp-uniform trip count
+        double x[K][3];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {                        // gathers first: 3K independent loads per lane
+            const int bi = g0 + k * cpw + c.sw;
+            const int cc = __shfl_sync(0xffffffffu, colreg, bi & 31);
+            x[k][0] = x[k][1] = x[k][2] = 0.0;
+            if (c.act && bi < nb) {
+                const double* xp = xc + (size_t)(3 * cc) * r + c.j;
+                x[k][0] = xp[0]; x[k][1] = xp[r]; x[k][2] = xp[2 * r];
+            }
         }
-        e0 = fma(q0[0], x0, e0); e0 = fma(q0[1], x1, e0); e0 = fma(q0[2], x2, e0);
-        e1 = fma(q1[0], x0, e1); e1 = fma(q1[1], x1, e1); e1 = fma(q1[2], x2, e1);
-        e2 = fma(q2[0], x0, e2); e2 = fma(q2[1], x1, e2); e2 = fma(q2[2], x2, e2);
-        c = cn;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int bi = g0 + k * cpw + c.sw;
+            if (bi < nb) {
+                const unsigned qa = sbuf + (unsigned)bi * 128u;
+                const double2 a0 = lds_v2(qa), a1 = lds_v2(qa + 16), b0 = lds_v2(qa + 32), b1 = lds_v2(qa + 48), c0 = lds_v2(qa + 64), c1 = lds_v2(qa + 80);
+                E[0] = fma(a0.x, x[k][0], E[0]); E[0] = fma(a0.y, x[k][1], E[0]); E[0] = fma(a1.x, x[k][2], E[0]);
+                E[1] = fma(b0.x, x[k][0], E[1]); E[1] = fma(b0.y, x[k][1], E[1]); E[1] = fma(b1.x, x[k][2], E[1]);
+                E[2] = fma(c0.x, x[k][0], E[2]); E[2] = fma(c0.y, x[k][1], E[2]); E[2] = fma(c1.x, x[k][2], E[2]);
+            }
+        }
     }
-    for (int off = W; off < 32; off <<= 1) {                 // fixed-order butterfly over the warp's sub-warps
-        e0 += shfl_xor_d(e0, off); e1 += shfl_xor_d(e1, off); e2 += shfl_xor_d(e2, off);
-    }
-    E[0] = e0; E[1] = e1; E[2] = e2;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------ per-camera epilogues
@@ -748,11 +801,34 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs&
     const int steps = d.ldq / 64;                           // k-split: contiguous runs of 64-column steps
     const int kbeg = (int)(((long long)ks * steps) / KS) * 64;
     const int kend = (int)(((long long)(ks + 1) * steps) / KS) * 64;
+    // block-CSR: the warp's chunk pipeline runs across the batches (the next row's first chunk is already in flight while the
+    // CTA finishes the current batch's epilogue)
+    BsrCursor cur{-1, 0, 0, 0};
+    int col_cur = 0, buf_cur = 0;
+    unsigned long long policy = 0;
+    bool bsr_ok = true;
+    if (BSR) {
+        policy = l2_policy_evict_first();
+        cur.cam = c.cam_lo + cslot; cur.q = ks;
+        bsr_seek(d, cur, c.cam_hi, ks, CB);
+        if (cur.valid()) col_cur = bsr_issue(c, cur, 0, policy);
+    }
     for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
         const int cam = b0 + cslot;
         if (BSR) {
             double E[3] = {0.0, 0.0, 0.0};
-            if (cam < c.cam_hi) qy_sweep_bsr(d, cam, ks, KS, c.W, c.cpw, c.sw, c.j, c.act, E);
+            while (bsr_ok && cur.valid() && cur.cam == cam) {                  // warp-uniform
+                BsrCursor nxt = cur;
+                nxt.q += KS;
+                bsr_seek(d, nxt, c.cam_hi, ks, CB);
+                int col_nxt = 0;
+                if (nxt.valid()) col_nxt = bsr_issue(c, nxt, buf_cur ^ 1, policy);
+                bsr_ok = bsr_consume(c, cur.count(), buf_cur, col_cur, E);
+                cur = nxt; col_cur = col_nxt; buf_cur ^= 1;
+            }
+            for (int off = c.W; off < 32; off <<= 1) {      // fixed-order butterfly over the warp's sub-warps
+                E[0] += shfl_xor_d(E[0], off); E[1] += shfl_xor_d(E[1], off); E[2] += shfl_xor_d(E[2], off);
+            }
             if (c.lane < c.W && c.j < RP) {                 // the warp's totals, column j: same slots warp_reduce_to_red fills
                 c.red[(c.warp * 3 + 0) * RP + c.j] = E[0]; c.red[(c.warp * 3 + 1) * RP + c.j] = E[1]; c.red[(c.warp * 3 + 2) * RP + c.j] = E[2];
             }
@@ -769,6 +845,7 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs&
         part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, min(CB, c.cam_hi - b0), KS, CB);
         __syncthreads();
     }
+    if (BSR && !bsr_ok && c.lane == 0) c.raise_abort();       // a bulk copy never completed: the next barrier fails everywhere
     return part;
 }
 
@@ -940,6 +1017,17 @@ __device__ __forceinline__ void ring_init(Ctx<RP, NT>& c, unsigned char* dyn_sme
         c.s6 = v6 - (long long)c.cam_lo * 6;
         const size_t bytes = (size_t)((kNumVecR * cpc * r3 + kNumVecS * cpc + 6 * cpc) * sizeof(double));
         base += (bytes + 127) & ~(size_t)127;
+    }
+    if (d.bsr_val) {          // block-CSR: two staged chunks + two mbarriers per warp
+        constexpr int NWARPS = NT / 32;
+        double* bufs = reinterpret_cast<double*>(base);
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufs + (size_t)NWARPS * 2 * kBsrChunk * 16);
+        c.bsr_buf = bufs + (size_t)c.warp * 2 * kBsrChunk * 16;
+        c.bsr_bar = bars + c.warp * 2;
+        if (c.lane == 0) { mbar_init(&c.bsr_bar[0], 1); mbar_init(&c.bsr_bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+        return;
     }
     if (!d.use_tma) { __syncthreads(); return; }
     c.ring = reinterpret_cast<double*>(base);
