@@ -357,7 +357,7 @@ static int make_map(xm_handle* h, CUtensorMap* m, const double* base, uint64_t c
 static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     Plan p{};
     p.RP = rank_pad(r);
-    p.NT = (p.RP <= 10) ? 512 : 256;
+    p.NT = (p.RP <= 10 || h->is_bsr) ? 512 : 256;      // dense sweeps hold 3 x RP accumulators per lane; block-CSR holds 3
     p.NW = p.NT / 32;
     p.W = 4; while (p.W < r) p.W <<= 1;
     p.cpw = 32 / p.W;
@@ -389,7 +389,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.vec_smem = (h->opt.vec_in_global == 0 && p.vec_bytes <= 64 * 1024) ? 1 : 0;
     if (p.vec_smem) budget -= p.vec_bytes;
     p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
-    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * (kBsrChunk * 128 + 8);      // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
+    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * kBsrChunk * 128;            // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
     if (p.use_tma) {
         p.nbmax = std::min(p.CB, cpc);
         p.stage_doubles = (3 * p.nbmax + p.RP) * p.KC;   // operand area sized for the padded rank (consumers read RP rows)

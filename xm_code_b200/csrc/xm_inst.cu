@@ -25,6 +25,20 @@ static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opco
     return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(NT), args, dyn, st);
 }
 
+// block-CSR kernels hold 3 accumulators per lane whatever the rank: 512 threads for every RP
+template <int RP>
+static cudaError_t launch_bsr(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, 512, 2> : (const void*)xm_ops_kernel<RP, 512, 2>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    if (kind == 0) {
+        void* args[] = {(void*)&d, (void*)h->mapQ, (void*)&h->mapX};
+        return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(512), args, dyn, st);
+    }
+    void* args[] = {(void*)&d, (void*)h->mapQ, (void*)&h->mapX, (void*)&opcode};
+    return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(512), args, dyn, st);
+}
+
 #if XM_INST_GROUP == 0
 cudaError_t xm_launch_group0(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
@@ -46,9 +60,9 @@ cudaError_t xm_launch_group1(int kind, int RP, const xm_handle* h, const Dev& d,
 #else
 cudaError_t xm_launch_group2(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
-        case 12: return launch_t<12, 256>(kind, h, d, opcode, dyn, st);
-        case 16: return launch_t<16, 256>(kind, h, d, opcode, dyn, st);
-        case 20: return launch_t<20, 256>(kind, h, d, opcode, dyn, st);
+        case 12: return d.bsr_val ? launch_bsr<12>(kind, h, d, opcode, dyn, st) : launch_t<12, 256>(kind, h, d, opcode, dyn, st);
+        case 16: return d.bsr_val ? launch_bsr<16>(kind, h, d, opcode, dyn, st) : launch_t<16, 256>(kind, h, d, opcode, dyn, st);
+        case 20: return d.bsr_val ? launch_bsr<20>(kind, h, d, opcode, dyn, st) : launch_t<20, 256>(kind, h, d, opcode, dyn, st);
     }
     return cudaErrorInvalidValue;
 }
