@@ -389,7 +389,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.vec_smem = (h->opt.vec_in_global == 0 && p.vec_bytes <= 64 * 1024) ? 1 : 0;
     if (p.vec_smem) budget -= p.vec_bytes;
     p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
-    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * kBsrChunk * 128;            // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
+    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * (kBsrChunk * 128 + 8);      // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
     if (p.use_tma) {
         p.nbmax = std::min(p.CB, cpc);
         p.stage_doubles = (3 * p.nbmax + p.RP) * p.KC;   // operand area sized for the padded rank (consumers read RP rows)
@@ -436,6 +436,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.partials = (double*)q;
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
     d.x_cam_major = h->is_bsr ? 1 : 0;
+    d.bsr_stage = 0; d.bsr_k8 = 0;          // measured best on B200 (profiles/r01_bsr_qy.md): bulk-TMA chunks, 4 gathers per sub-warp
+    if (const char* e = getenv("XM_TUNE_BSR")) { const int v = atoi(e); d.bsr_stage = v & 1; d.bsr_k8 = (v >> 1) & 1; }      // A/B hook
     d.Q = h->is_bsr ? nullptr : h->Qp;
     if (h->is_bsr) { d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim; }   // else null: dense
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;

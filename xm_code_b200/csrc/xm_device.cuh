@@ -87,6 +87,7 @@ struct Dev {
     int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
     int profile;               // fine-grained phase timers on (costs a few percent)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
+    int bsr_stage, bsr_k8;     // block-CSR staging: 0 = one bulk-TMA copy per chunk, 1 = cp.async; gathers in flight per sub-warp: 4 or 8
     int x_cam_major;           // operand layout: 0 = j-major Xt[j*ldq + row] (dense paths, TMA boxes), 1 = camera-major Xt[row*r + j]
                                // (block-CSR: the 3r doubles a block needs are contiguous)
     double *partials;          // kPartialBufs * (G + 1) * kPartialStride: the reduction slots of THIS GPU's CTAs
@@ -163,6 +164,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(col0), "r"(row0), "r"(smem_u32(bar)) : "memory");
 }
+// 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void tma_load_1d_stream(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 // 16 bytes global -> shared without registers (LDGSTS, L1 bypass).  L2 evict_first: the blocks of Q are read once per
 // product and must not push the (heavily re-read) operand out of L2.
 __device__ __forceinline__ void cp_async16_stream(unsigned dst_smem, const void* src, unsigned long long policy) {
@@ -233,7 +239,7 @@ struct Ctx {
     // TMA ring state (grid-uniform): running use counter (stage = g % ST, parity = (g / ST) & 1) and how many of the
     // next phase's uses already have their Q tiles in flight (cross-phase prefetch)
     double* ring; unsigned long long *fullQ, *fullX, *empty;
-    double* bsr_buf;            // block-CSR: this warp's two staged chunks of blocks
+    double* bsr_buf; unsigned long long* bsr_bar; unsigned bsr_phase;   // block-CSR: this warp's two staged chunks, their mbarriers, parity bits
     unsigned g_use; int prefetched;
     double* red;                // smem [NWARPS][3][RP]
     double* bsum;               // smem [NWARPS]
@@ -258,7 +264,7 @@ struct Ctx {
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
         ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
-        bsr_buf = nullptr;
+        bsr_buf = nullptr; bsr_bar = nullptr; bsr_phase = 0;
     }
     // end of a launch: remember the epoch for the next one (every CTA has long read epoch_store by now: it sits behind at
     // least one barrier whenever the value changes)
@@ -622,21 +628,23 @@ __device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, 
 // Block-CSR Q.Y: one warp per block row (camera), blocks stored 4x4 row-major = one 128-byte line each (row / column 3 are
 // zero padding for bdim == 3), operand CAMERA-MAJOR (Xt[(3c+a) r + j]: the 3r doubles a block needs are adjacent).
 //
-//   * Q blocks: the warp stages its row through shared memory in chunks of kBsrChunk = 32 blocks (4 KB): eight warp-wide
-//     16-byte cp.async (LDGSTS, L1 bypass, L2 evict_first) into one of the warp's two buffers, one commit group per chunk;
+//   * Q blocks: the warp stages its row through shared memory in chunks of kBsrChunk = 32 blocks — ONE 4 KB bulk copy (1-D TMA,
+//     cp.async.bulk, L2 evict_first) per chunk into one of the warp's two buffers, completion on the warp's own mbarrier;
 //     the next chunk (of this row, or the first of the warp's next row) is in flight while the current one is consumed, so
-//     ~64 KB of Q per SM are in flight without holding a register.  (One 4 KB bulk-TMA copy per chunk was measured first:
-//     the SM's TMA unit retires one bulk op per ~140 ns whatever its size — 2175 chunks per SM per product put a 0.30 ms
-//     floor under a 0.21 ms roofline; a CTA-wide ring with large ops would need rows split across warps.)  The 32 column
-//     indices of a chunk are one coalesced load (one per lane), handed out by shuffles.
+//     ~64 KB of Q per SM are in flight without holding a register.  (bsr_stage = 1 stages with eight warp-wide 16-byte
+//     cp.async instead: measured 5-12 % slower.)  The 32 column indices of a chunk are one coalesced load (one per lane),
+//     handed out by shuffles.
 //   * operand gather: the warp's sub-warps (W lanes, the geometry of every per-camera phase) deal the chunk's blocks out
-//     round-robin; lane j of a sub-warp owns column j.  Four to eight blocks per sub-warp are gathered at once (12-24 independent loads
+//     round-robin; lane j of a sub-warp owns column j.  Four blocks per sub-warp are gathered at once (12 independent loads
 //     per lane, each contiguous across the sub-warp: 11 sectors per block at r = 10 against 36 with the j-major layout of
 //     the dense paths), then multiplied with the block read from shared memory (LDS broadcasts).
 //   * the 3 x r result of the row ends up as 3 registers per lane after a fixed-order butterfly over the sub-warps —
 //     the layout the per-camera epilogue wants.
 // History (profiles/r01_bsr_qy.md): v1 lane-per-block with j-major operand was L1TEX-bound (81 %, 371 M sectors); v2 (this
-// mapping, blocks through registers) and v3 (+ L2 prefetch of the next row) were latency-bound at 16 warps per SM.
+// mapping, blocks through registers) and v3 (+ L2 prefetch of the next row) were latency-bound at 16 warps per SM.  What
+// bounds this version on an Erdos-Renyi graph is the L2 -> SM fabric: every block needs 24 r operand bytes from L2 on top
+// of its own 128 B (no locality to exploit: each camera's row is read by ~100 random rows), and Q + gathers together move
+// at ~5.5 TB/s for r = 5, 10 and 20 alike; eight gathers in flight instead of four is slower.
 struct BsrCursor {           // the warp's position in its sequence of chunks: rows cam, cam + CB, ... ; chunks part, part + nparts, ...
     int cam, q, rb0, rb1;
     __device__ __forceinline__ bool valid() const { return cam >= 0; }
@@ -656,6 +664,13 @@ __device__ __forceinline__ int bsr_issue(C& c, const BsrCursor& cu, int buf, uns
     const Dev& d = c.d;
     const int st = cu.start(), nb = cu.count();
     __syncwarp();                                            // every lane is done with the buffer's previous chunk
+    if (d.bsr_stage == 0) {                                  // one bulk-TMA copy per chunk
+        if (c.lane == 0) {
+            mbar_expect_tx(&c.bsr_bar[buf], (unsigned)nb * 128u);
+            tma_load_1d_stream(c.bsr_buf + (size_t)buf * kBsrChunk * 16, d.bsr_val + (size_t)st * 16, (unsigned)nb * 128u, &c.bsr_bar[buf], policy);
+        }
+        return (c.lane < nb) ? __ldg(d.bsr_col + st + c.lane) : 0;
+    }
     const unsigned dst = smem_u32(c.bsr_buf + (size_t)buf * kBsrChunk * 16) + (unsigned)c.lane * 16u;
     const char* src = reinterpret_cast<const char*>(d.bsr_val + (size_t)st * 16) + c.lane * 16;
     const int nbytes = nb * 128;
@@ -671,8 +686,13 @@ template <int K, class C>
 __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, bool more_in_flight, double (&E)[3]) {
     const Dev& d = c.d;
     const int r = d.r, cpw = c.cpw;
-    if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
-    __syncwarp();                                            // the lanes' copies are visible to the whole warp
+    if (d.bsr_stage == 0) {
+        (void)mbar_wait(&c.bsr_bar[buf], (c.bsr_phase >> buf) & 1u);
+        c.bsr_phase ^= 1u << buf;
+    } else {
+        if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();                                        // the lanes' copies are visible to the whole warp
+    }
     const unsigned sbuf = smem_u32(c.bsr_buf + (size_t)buf * kBsrChunk * 16);
     const double* xc = d.Xt;
     for (int g0 = 0; g0 < nb; g0 += K * cpw) {               // warp-uniform trip count
@@ -828,8 +848,8 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs&
                 bsr_seek(d, nxt, c.cam_hi, ks, CB);
                 int col_nxt = 0;
                 if (nxt.valid()) col_nxt = bsr_issue(c, nxt, buf_cur ^ 1, policy);
-                if (c.cpw <= 2) bsr_consume<8>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);     // few sub-warps: deeper gather
-                else            bsr_consume<4>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+                if (d.bsr_k8) bsr_consume<8>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);       // deeper gather
+                else          bsr_consume<4>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
                 cur = nxt; col_cur = col_nxt; buf_cur ^= 1;
             }
             for (int off = c.W; off < 32; off <<= 1) {      // fixed-order butterfly over the warp's sub-warps
@@ -1023,8 +1043,14 @@ __device__ __forceinline__ void ring_init(Ctx<RP, NT>& c, unsigned char* dyn_sme
         const size_t bytes = (size_t)((kNumVecR * cpc * r3 + kNumVecS * cpc + 6 * cpc) * sizeof(double));
         base += (bytes + 127) & ~(size_t)127;
     }
-    if (d.bsr_val) {          // block-CSR: two staged chunks per warp
-        c.bsr_buf = reinterpret_cast<double*>(base) + (size_t)c.warp * 2 * kBsrChunk * 16;
+    if (d.bsr_val) {          // block-CSR: two staged chunks + two mbarriers per warp
+        constexpr int NWARPS = NT / 32;
+        double* bufs = reinterpret_cast<double*>(base);
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufs + (size_t)NWARPS * 2 * kBsrChunk * 16);
+        c.bsr_buf = bufs + (size_t)c.warp * 2 * kBsrChunk * 16;
+        c.bsr_bar = bars + c.warp * 2;
+        if (c.lane == 0) { mbar_init(&c.bsr_bar[0], 1); mbar_init(&c.bsr_bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
         return;
     }
