@@ -279,7 +279,7 @@ def run_reference(args):
     except Exception:
         pass
     base = {"metric": "xm_tcg_iterations_per_sec", "unit": "tCG iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference"}
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference"}
     if have_gpu and os.path.exists(harness):
         from xm_code_b200 import binio
         d = tempfile.mkdtemp()

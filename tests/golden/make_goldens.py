@@ -4,6 +4,7 @@
   simple1_Q.bin            copy of the reference's shipped input assets/SIMPLE1/Q.bin (447 x 447, data fixture)
   simple2_obs.npz          SIMPLE2 observations after the preprocessing of 2_test_creatematrix.py:29-144
                            (edges 1-based like the reference, weights, camera-frame points) + ground-truth rotations
+  simple2_frames.npz       original frame index of every re-indexed camera (to line gtR up with the solver's camera order)
   simple2_Q_ref.npz        Q (279 x 279) produced by the reference's own utils/creatematrix.create_matrix on them
   recover_ref.npz          inputs/outputs of the reference's own utils/recoversolution.recover_XM (24 cameras, Q and Abar
                            from the reference's create_matrix): rank-3, rank-5 and mirrored cases
@@ -61,11 +62,27 @@ def preprocess(data):
     return edges, weights, pts, N, M
 
 
+def frame_permutation(data):
+    """orig_of_new[i] = original (0-based) frame index of re-indexed camera i: the preprocessing swaps the most-observed frame
+    with frame 0 (2_test_creatematrix.py:74-110); ground truth files are in the original order."""
+    edges = data[:, :2].astype(int)
+    _, uniq = np.unique(edges, axis=0, return_index=True)
+    edges = edges[uniq]
+    N = int(edges[:, 0].max())
+    cnt = np.bincount(edges[:, 0] - 1, minlength=N)
+    assert np.all(cnt > 0)
+    maxf = int(np.argmax(cnt))
+    orig = np.arange(N)
+    orig[0], orig[maxf] = maxf, 0
+    return orig
+
+
 def main():
     shutil.copyfile(f"{REF}/assets/SIMPLE1/Q.bin", f"{HERE}/simple1_Q.bin")
     data = load_bin(f"{REF}/assets/SIMPLE2/landmark.bin")
     edges, weights, pts, N, M = preprocess(data)
     gtR = load_bin(f"{REF}/assets/SIMPLE2/gtR.bin")
+    np.savez(f"{HERE}/simple2_frames.npz", orig_of_new=frame_permutation(data))
     np.savez_compressed(f"{HERE}/simple2_obs.npz", edges=edges.astype(np.int32), weights=weights, pts=pts.astype(np.float64),
                         N=N, M=M, gtR=gtR)
     from utils.creatematrix import create_matrix

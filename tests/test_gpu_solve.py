@@ -155,3 +155,37 @@ def test_full_size_properties_bal_shaped(gpu_handle_factory):
     _, _, gn = h.rgrad(a.R, a.s, 0.0)
     assert gn < 1e-6
     assert np.max(np.abs(a.s - prob["s"])) < 0.15               # recovers the ground-truth scales up to noise
+
+
+def test_simple2_pipeline_end_to_end(tmp_path, simple2_obs, gpu_handle_factory):
+    """BASELINE config 2 — what 2_test_creatematrix.py does: observations -> create_matrix -> Q.bin / Abar.bin ->
+    XM.solve(path, 5, 1e-1, 0, 1000) (compiled module) -> R.bin / s.bin -> recover_XM (GPU) -> rotations against the shipped
+    ground truth gtR (relative to camera 1; SURVEY.md §8c: median 0.09 deg, max 0.9 deg at this tolerance)."""
+    from xm_code_b200 import binio, creatematrix
+    from xm_code_b200.recover import recover_XM
+    o = simple2_obs
+    N, M = int(o["N"]), int(o["M"])
+    d = tmp_path / "SIMPLE2"
+    d.mkdir()
+    creatematrix.create_matrix(o["weights"], o["edges"], o["pts"], str(d))
+    code = "import sys; sys.path.append(%r); import XM; XM.solve(%r, 5, 1e-1, 0.0, 1000)" % (os.path.join(ROOT, "XM", "build"), str(d))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    R = binio.load_matrix_from_bin(str(d / "R.bin")); s = binio.load_matrix_from_bin(str(d / "s.bin"))
+    Q = binio.load_matrix_from_bin(str(d / "Q.bin")); Abar = binio.load_matrix_from_bin(str(d / "Abar.bin"))
+    assert R.shape[0] == 3 * N and R.shape[1] in (3, 4) and s.shape == (N, 1)        # certified at rank 3 or 4 (SURVEY App. A)
+    R_real, s_real, p_est, t_est = recover_XM(Q, R, s, Abar, 0.0, handle=gpu_handle_factory())
+    assert R_real.shape == (3, 3 * N) and p_est.shape == (3, M) and t_est.shape == (3, N)
+    orig = np.load(os.path.join(ROOT, "tests", "golden", "simple2_frames.npz"))["orig_of_new"]
+    G = o["gtR"].reshape(3, -1, 3).transpose(1, 0, 2)[orig]
+    Rb = R_real.reshape(3, N, 3).transpose(1, 0, 2)
+    err = []
+    for i in range(N):
+        c = (np.trace(Rb[i].T @ (G[0] @ G[i].T)) - 1.0) / 2.0
+        err.append(np.degrees(np.arccos(np.clip(c, -1.0, 1.0))))
+    assert np.median(err) < 0.2 and np.max(err) < 1.5, (np.median(err), np.max(err))
+    assert abs(np.mean(s_real) - 1.0) < 0.01 and np.all(s_real > 0.9) and np.all(s_real < 1.1)
+    # and the recovery agrees with the oracle's restatement of recover_XM on the same solver output
+    ref = xo.recover(R, s[:, 0], Abar)
+    np.testing.assert_allclose(R_real, ref["R"], atol=1e-10)
+    np.testing.assert_allclose(t_est, ref["t"], atol=1e-8 * max(1.0, np.abs(ref["t"]).max()))
