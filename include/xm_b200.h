@@ -12,6 +12,7 @@
  *   xm_certify          <- checkeig(C,sR,lam,v,primal)                                          XM/include/XM/checkeig.h:42-368
  *   xm_escape_scale     <- DecentDirectionKernal                                                XM/src/XM_main.cu:8-16
  *   xm_recover          <- recover_XM(Q,R,s,Abar,lam)                                           utils/recoversolution.py:4-86
+ *   xm_residuals        <- the per-observation error of the XM^2 outlier cut                    3_test_colmap_glomap.py:304-316
  *
  * Matrix arguments use the reference's wire layouts: R is 3N x r COLUMN-MAJOR with
  * rows 3i..3i+2 = camera i; s is length N with s[0] == 1 (the reference's s_ex); v is length 3N.
@@ -171,6 +172,10 @@ int  xm_certify(xm_handle* h, int r, const double* R, const double* s, double la
  * The reference's Q and lam arguments only feed a printed diagnostic and are not needed.  Works on any handle (no Q). */
 int  xm_recover(xm_handle* h, int n_cameras, int r, const double* R, const double* s, const double* Abar, int64_t abar_rows,
                 double* R_out, double* s_out, double* y_out, double* eig_out, int* negative_out);
+/* XM^2 outlier cut: err[o] = w[o] * || p[:, lm[o]] - (s[cam[o]] R_cam[o] pt[o] + t[:, cam[o]]) ||^2 for every observation
+ * (cam, lm 0-based int32; pts n_obs x 3 ROW-major; R_real 3 x 3N, t 3 x N, p 3 x M column-major as returned by xm_recover). */
+int  xm_residuals(xm_handle* h, int64_t n_obs, int n_cameras, int n_landmarks, const int* cam, const int* lm, const double* pts,
+                  const double* w, const double* R_real, const double* s_real, const double* t, const double* p, double* err_out);
 /* v[3i..3i+2] /= s[i]  (DecentDirectionKernal) — host-side helper, trivial. */
 int  xm_escape_scale(int n_cameras, double* v, const double* s);
 

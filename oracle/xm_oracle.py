@@ -481,6 +481,17 @@ def recover(R, s, Abar=None):
     return out
 
 
+def observation_errors(edges, landmarks, weights, R_real, s_real, t_est, p_est):
+    """Per-observation weighted squared residual of the XM^2 outlier cut, as written in the reference's pipeline script
+    (3_test_colmap_glomap.py:304-316).  edges: (n, 2) 1-based (camera, landmark)."""
+    N = np.asarray(s_real).shape[0]
+    src = np.asarray(edges)[:, 0] - 1; dst = np.asarray(edges)[:, 1] - 1
+    Rm = np.asarray(R_real).reshape(3, N, 3).transpose(1, 0, 2)[src]
+    moved = np.asarray(s_real)[src, None] * np.einsum("nij,nj->ni", Rm, landmarks) + np.asarray(t_est)[:, src].T
+    diff = np.asarray(p_est)[:, dst].T - moved
+    return np.asarray(weights) * np.sum(diff ** 2, axis=1)
+
+
 # --------------------------------------------------------------------------- .bin wire format (utils/io.py:17-58)
 def load_bin(path):
     with open(path, "rb") as f:

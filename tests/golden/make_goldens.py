@@ -6,6 +6,7 @@
                            (edges 1-based like the reference, weights, camera-frame points) + ground-truth rotations
   simple2_frames.npz       original frame index of every re-indexed camera (to line gtR up with the solver's camera order)
   simple2_Q_ref.npz        Q (279 x 279) produced by the reference's own utils/creatematrix.create_matrix on them
+  checklandmarks_ref.npz   inputs/outputs of the reference's own utils/checkconnection.checklandmarks on two random graphs
   recover_ref.npz          inputs/outputs of the reference's own utils/recoversolution.recover_XM (24 cameras, Q and Abar
                            from the reference's create_matrix): rank-3, rank-5 and mirrored cases
 """
@@ -140,9 +141,46 @@ def make_recover_goldens():
     print("recover goldens: N", N, "M", M, "Abar", Abar.shape)
 
 
+
+
+def make_checklandmarks_goldens():
+    """checklandmarks_ref.npz: inputs and outputs of the reference's OWN utils/checkconnection.checklandmarks on two random
+    bipartite graphs: (a) under-observed frames, landmarks seen once, the most-observed frame not first; (b) additionally two
+    disconnected clusters (the largest-component branch)."""
+    from utils.checkconnection import checklandmarks
+    out = {}
+    for tag, seed, split in (("a", 1, False), ("b", 2, True)):
+        rng = np.random.default_rng(seed)
+        N, M = 40, 300
+        rows = []
+        for i in range(N):
+            k = int(rng.integers(3, 9)) if i % 7 == 3 else int(rng.integers(14, 40))     # some frames stay under the threshold of 10
+            if i == 11:
+                k = 80                                                                    # the most-observed frame is not frame 0
+            if split:
+                pool = np.arange(0, 200) if i < 28 else np.arange(200, 300)               # two clusters that share nothing
+            else:
+                pool = np.arange(M)
+            for l in rng.choice(pool, size=min(k, pool.size), replace=False):
+                rows.append((i + 1, int(l) + 1))
+        edges = np.array(rows, dtype=int)
+        n = edges.shape[0]
+        landmarks = rng.standard_normal((n, 3)); weights = rng.uniform(0.5, 2.0, n); rgbs = rng.integers(0, 255, (n, 3))
+        with contextlib.redirect_stdout(io.StringIO()):
+            e2, l2, w2, c2, ind = checklandmarks(edges.copy(), landmarks.copy(), weights.copy(), rgbs.copy(), N, M)
+        out.update({f"{tag}_edges_in": edges, f"{tag}_landmarks_in": landmarks, f"{tag}_weights_in": weights, f"{tag}_rgbs_in": rgbs,
+                    f"{tag}_N": N, f"{tag}_M": M, f"{tag}_edges": e2, f"{tag}_landmarks": l2, f"{tag}_weights": w2, f"{tag}_rgbs": c2,
+                    f"{tag}_indices": ind})
+        print("checklandmarks golden", tag, edges.shape, "->", e2.shape, "frames", int(e2[:, 0].max()), "landmarks", int(e2[:, 1].max()))
+    np.savez_compressed(f"{HERE}/checklandmarks_ref.npz", **out)
+
+
 if __name__ == "__main__":
     if "--recover" in sys.argv:          # only the recover_XM fixture
         make_recover_goldens()
+    elif "--checklandmarks" in sys.argv:
+        make_checklandmarks_goldens()
     else:
         main()
         make_recover_goldens()
+        make_checklandmarks_goldens()

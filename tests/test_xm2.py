@@ -1,0 +1,110 @@
+"""XM^2 outer loop: graph clean-up against outputs of the reference's own checklandmarks, the outlier
+rule, the per-observation residual kernel against the oracle, and the two-pass loop end to end on a corrupted problem."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import xm_oracle as xo
+from conftest import GOLD, ROOT
+from xm_code_b200 import problems, xm2
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_check_landmarks_matches_reference_output(tag):
+    g = np.load(os.path.join(GOLD, "checklandmarks_ref.npz"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        e, l, w, c, ind = xm2.check_landmarks(g[tag + "_edges_in"], g[tag + "_landmarks_in"], g[tag + "_weights_in"], g[tag + "_rgbs_in"],
+                                              int(g[tag + "_N"]), int(g[tag + "_M"]))
+    np.testing.assert_array_equal(e, g[tag + "_edges"])
+    np.testing.assert_array_equal(l, g[tag + "_landmarks"])
+    np.testing.assert_array_equal(w, g[tag + "_weights"])
+    np.testing.assert_array_equal(c, g[tag + "_rgbs"])
+    np.testing.assert_array_equal(ind, g[tag + "_indices"])
+    # the result is a clean problem: compact 1-based indices, every camera > 0 observations, every landmark >= 2, connected
+    assert e[:, 0].min() == 1 and e[:, 1].min() == 1
+    assert np.all(np.bincount(e[:, 0] - 1) > 0) and np.all(np.bincount(e[:, 1] - 1) >= 2)
+    assert ind[np.argmax(np.bincount(g[tag + "_edges_in"][:, 0] - 1))] == 0          # the most-observed frame is the anchor
+
+
+def test_check_landmarks_is_identity_on_a_clean_graph():
+    prob = problems.synthetic_sfm(20, n_landmarks=120, obs_per_camera=30, seed=3)
+    edges = np.stack([prob["cam"] + 1, prob["lm"] + 1], axis=1)
+    # make camera 0 the most observed so that no swap happens
+    with contextlib.redirect_stdout(io.StringIO()):
+        e, l, w, c, ind = xm2.check_landmarks(edges, prob["pt"], prob["w"], np.zeros((edges.shape[0], 3)), prob["N"], prob["M"])
+    assert e.shape == edges.shape and np.count_nonzero(ind < 0) == 0
+    assert sorted(ind.tolist()) == list(range(prob["N"]))
+
+
+def test_outlier_cut_is_the_90th_percentile_rule():
+    rng = np.random.default_rng(0)
+    err = rng.random(1000)
+    rm = xm2.outlier_cut(err)
+    assert rm.size == 100 and err[rm].min() > np.delete(err, rm).max()
+
+
+def test_oracle_observation_errors_vanish_at_the_noise_free_truth():
+    prob = problems.synthetic_sfm(15, n_landmarks=90, obs_per_camera=25, seed=4, noise=0.0)
+    N = prob["N"]
+    R_real = np.concatenate([prob["R"][i] for i in range(N)], axis=1)            # 3 x 3N, camera i = columns 3i..3i+2
+    edges = np.stack([prob["cam"] + 1, prob["lm"] + 1], axis=1)
+    err = xo.observation_errors(edges, prob["pt"], prob["w"], R_real, prob["s"], prob["t"].T, prob["p"].T)
+    assert err.shape == (edges.shape[0],) and err.max() < 1e-20
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path
+@pytest.mark.gpu
+def test_gpu_residuals_match_oracle(gpu_handle_factory):
+    rng = np.random.default_rng(5)
+    N, M, n = 37, 211, 5000
+    cam = rng.integers(0, N, n); lm = rng.integers(0, M, n)
+    edges = np.stack([cam + 1, lm + 1], axis=1)
+    pts = rng.standard_normal((n, 3)); w = rng.uniform(0.1, 2.0, n)
+    Rb = xo.mgs_rows(rng.standard_normal((N, 3, 3)))
+    R_real = Rb.transpose(1, 0, 2).reshape(3, 3 * N)
+    s = rng.uniform(0.5, 1.5, N); t = rng.standard_normal((3, N)); p = rng.standard_normal((3, M))
+    ref = xo.observation_errors(edges, pts, w, R_real, s, t, p)
+    got = xm2.observation_errors(edges, pts, w, R_real, s, t, p, handle=gpu_handle_factory())
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13 * ref.max())
+    from xm_code_b200 import capi
+    with pytest.raises(capi.XmError):                                            # out-of-range index is refused, not read
+        gpu_handle_factory().residuals(np.array([N]), np.array([0]), pts[:1], w[:1], R_real, s, t, p)
+
+
+@pytest.mark.gpu
+def test_xm2_refine_removes_planted_outliers(tmp_path, gpu_handle_factory):
+    """Two-pass loop on a 30-camera problem with 4 % grossly wrong observations: the first pass's 10 % cut must contain
+    (almost) all of them and the second pass must land closer to the ground-truth rotations than the first."""
+    sys.path.append(os.path.join(ROOT, "XM", "build"))
+    import XM
+    prob = problems.synthetic_sfm(30, n_landmarks=260, obs_per_camera=60, seed=9)
+    N, M = prob["N"], prob["M"]
+    rng = np.random.default_rng(1)
+    pts = prob["pt"].copy()
+    bad = rng.choice(pts.shape[0], size=pts.shape[0] // 25, replace=False)
+    pts[bad] += 0.5 * rng.standard_normal((bad.size, 3))
+    edges = np.stack([prob["cam"] + 1, prob["lm"] + 1], axis=1)
+    rgbs = np.arange(edges.shape[0])[:, None].repeat(3, axis=1)                  # carries the original observation id through
+    h = gpu_handle_factory()
+    d = tmp_path / "xm2"
+    d.mkdir()
+    out = xm2.refine(edges, pts, prob["w"], rgbs, N, M, str(d), solver=XM, handle=h)
+    kept = set(out["rgbs"][:, 0].tolist())
+    assert len(kept) <= 0.91 * edges.shape[0]
+    assert sum(int(b) in kept for b in bad) <= 0.15 * bad.size                   # the planted outliers are gone
+    assert np.count_nonzero(out["frame_map"] < 0) == 0                           # no camera was lost
+    # rotations against the ground truth (same convention as the SIMPLE2 test: R_real_i ~ G_1 G_i^T with G = R^T here)
+    fm = out["frame_map"]
+    Rb = out["R"].reshape(3, -1, 3).transpose(1, 0, 2)
+    G = prob["R"]                                                               # world-from-camera
+    anchor = int(np.flatnonzero(fm == 0)[0])
+    err = []
+    for i in range(N):
+        rel = G[anchor].T @ G[i]
+        c = (np.trace(Rb[fm[i]].T @ rel) - 1.0) / 2.0
+        err.append(np.degrees(np.arccos(np.clip(c, -1.0, 1.0))))
+    assert np.median(err) < 1.0, np.median(err)

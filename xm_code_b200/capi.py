@@ -43,7 +43,7 @@ EXPORTS = [
     "xm_op_objective", "xm_op_rgrad", "xm_op_rhess", "xm_op_retract", "xm_certify", "xm_escape_scale", "xm_bench_qy",
     "xm_bench_barrier", "xm_debug_trace",
     "xm_partition", "xm_comm_init", "xm_comm_connect", "xm_comm_connect_ptrs", "xm_comm_arena", "xm_comm_info", "xm_comm_reset", "xm_comm_disconnect",
-    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover", "xm_debug_counters",
+    "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover", "xm_residuals", "xm_debug_counters",
 ]
 XM_IPC_HANDLE_BYTES = 64
 XM_MAX_WORLD = 8
@@ -101,6 +101,7 @@ def load(path: str | None = None):
     lib.xm_set_q_dense_slab.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
     lib.xm_set_q_dense_slab_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
     lib.xm_recover.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp, ip]
+    lib.xm_residuals.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("xm_default_options", "xm_last_error", "xm_comm_arena"):
@@ -343,6 +344,17 @@ class Handle:
         if y is not None:
             out["t"] = y[:, :N]; out["p"] = y[:, N:]
         return out
+
+    def residuals(self, cam, lm, pts, w, R_real, s_real, t, p):
+        """xm_residuals: weighted squared residual per observation (cam, lm 0-based)."""
+        cam = np.ascontiguousarray(cam, dtype=np.int32); lm = np.ascontiguousarray(lm, dtype=np.int32)
+        pts = np.ascontiguousarray(pts, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64)
+        R_real = _f64(R_real); t = _f64(t); p = _f64(p); s_real = _f64(np.asarray(s_real).reshape(-1))
+        N = s_real.size; M = p.shape[1]
+        err = np.empty(cam.size)
+        self._check(self.lib.xm_residuals(self._h, cam.size, N, M, _ptr(cam), _ptr(lm), _ptr(pts), _ptr(w), _ptr(R_real), _ptr(s_real),
+                                          _ptr(t), _ptr(p), _ptr(err)), "xm_residuals")
+        return err
 
     def certify(self, R, s, lam, primal):
         R = _f64(R); s = _f64(s)

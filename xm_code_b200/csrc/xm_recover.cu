@@ -211,6 +211,27 @@ __global__ void abar_reduce_kernel(const double* __restrict__ part, long long ro
     o[0] = a0; o[1] = a1; o[2] = a2;
 }
 
+// ---- XM^2 support: weighted squared residual of every observation (3_test_colmap_glomap.py:304-316)
+//      err[o] = w[o] * || p[:, lm[o]] - ( s[cam[o]] * R_cam[o] * pt[o] + t[:, cam[o]] ) ||^2 ,  R_cam = R_real[:, 3 cam .. 3 cam + 2]
+__global__ void residuals_kernel(long long n_obs, const int* __restrict__ cam, const int* __restrict__ lm, const double* __restrict__ pts,
+                                 const double* __restrict__ w, const double* __restrict__ R, const double* __restrict__ s,
+                                 const double* __restrict__ t, const double* __restrict__ p, double* __restrict__ err) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_obs) return;
+    const int i = cam[o], k = lm[o];
+    const double x0 = pts[3 * o], x1 = pts[3 * o + 1], x2 = pts[3 * o + 2];
+    const double* Ri = R + (size_t)9 * i;                    // column-major 3 x 3 block: Ri[row + 3 col]
+    const double si = s[i];
+    double e = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double y = si * (Ri[a] * x0 + Ri[a + 3] * x1 + Ri[a + 6] * x2) + t[(size_t)3 * i + a];
+        const double dlt = p[(size_t)3 * k + a] - y;
+        e = fma(dlt, dlt, e);
+    }
+    err[o] = w[o] * e;
+}
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -271,5 +292,34 @@ extern "C" int xm_recover(xm_handle* h, int N, int r, const double* R, const dou
     XM_CUDA(h, cudaMemcpyAsync(&neg, dneg.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     XM_CUDA(h, cudaStreamSynchronize(st));
     if (negative_out) *negative_out = neg;
+    return XM_OK;
+}
+
+extern "C" int xm_residuals(xm_handle* h, int64_t n_obs, int N, int M, const int* cam, const int* lm, const double* pts, const double* w,
+                            const double* R_real, const double* s_real, const double* t, const double* p, double* err_out) {
+    if (!h || n_obs <= 0 || N <= 0 || M <= 0 || !cam || !lm || !pts || !w || !R_real || !s_real || !t || !p || !err_out) return XM_EINVAL;
+    for (int64_t o = 0; o < n_obs; ++o)
+        if (cam[o] < 0 || cam[o] >= N || lm[o] < 0 || lm[o] >= M) { h->err = "xm_residuals: observation index out of range"; return XM_EINVAL; }
+    XM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    DevBuf dcam, dlm, dpts, dw, dR, ds, dt, dp, derr;
+    XM_CUDA(h, dcam.alloc(sizeof(int) * n_obs)); XM_CUDA(h, dlm.alloc(sizeof(int) * n_obs)); XM_CUDA(h, dpts.alloc(sizeof(double) * 3 * n_obs));
+    XM_CUDA(h, dw.alloc(sizeof(double) * n_obs)); XM_CUDA(h, derr.alloc(sizeof(double) * n_obs));
+    XM_CUDA(h, dR.alloc(sizeof(double) * 9 * N)); XM_CUDA(h, ds.alloc(sizeof(double) * N)); XM_CUDA(h, dt.alloc(sizeof(double) * 3 * N));
+    XM_CUDA(h, dp.alloc(sizeof(double) * 3 * M));
+    XM_CUDA(h, cudaMemcpyAsync(dcam.p, cam, sizeof(int) * n_obs, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(dlm.p, lm, sizeof(int) * n_obs, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(dpts.p, pts, sizeof(double) * 3 * n_obs, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(dw.p, w, sizeof(double) * n_obs, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(dR.p, R_real, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(ds.p, s_real, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(dt.p, t, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+    XM_CUDA(h, cudaMemcpyAsync(dp.p, p, sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
+    residuals_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, st>>>(n_obs, dcam.as<int>(), dlm.as<int>(), dpts.as<double>(), dw.as<double>(),
+                                                                     dR.as<double>(), ds.as<double>(), dt.as<double>(), dp.as<double>(), derr.as<double>());
+    XM_CUDA(h, cudaGetLastError());
+    h->launches++;
+    XM_CUDA(h, cudaMemcpyAsync(err_out, derr.p, sizeof(double) * n_obs, cudaMemcpyDeviceToHost, st));
+    XM_CUDA(h, cudaStreamSynchronize(st));
     return XM_OK;
 }
