@@ -79,8 +79,24 @@ def test_gpu_residuals_match_oracle(gpu_handle_factory):
 def test_xm2_refine_removes_planted_outliers(tmp_path, gpu_handle_factory):
     """Two-pass loop on a 30-camera problem with 4 % grossly wrong observations: the first pass's 10 % cut must contain
     (almost) all of them and the second pass must land closer to the ground-truth rotations than the first."""
-    sys.path.append(os.path.join(ROOT, "XM", "build"))
-    import XM
+    import subprocess
+
+    class XM:            # the compiled module, one interpreter per call like the reference's scripts (and the other tests here)
+        @staticmethod
+        def _run(fn, path, max_rank, tol, lam, max_time):
+            code = "import sys; sys.path.append(%r); import XM; XM.%s(%r, %d, %r, %r, %r)" % (
+                os.path.join(ROOT, "XM", "build"), fn, path, max_rank, tol, lam, max_time)
+            out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0, out.stderr[-2000:]
+
+        @classmethod
+        def solve(cls, *a):
+            cls._run("solve", *a)
+
+        @classmethod
+        def solve_rank3(cls, *a):
+            cls._run("solve_rank3", *a)
+
     prob = problems.synthetic_sfm(30, n_landmarks=260, obs_per_camera=60, seed=9)
     N, M = prob["N"], prob["M"]
     rng = np.random.default_rng(1)

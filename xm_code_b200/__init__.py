@@ -5,6 +5,8 @@ Host-side Python mirror of the reference surface for this path only:
   * ``capi``      ctypes binding of the C-ABI (include/xm_b200.h, libxm_b200.so) — what tests and bench.py call
   * ``dist``      torch.distributed plumbing for one solve partitioned by camera over the GPUs of a node
   * ``recover``   ``recover_XM`` with the reference's signature (utils/recoversolution.py:4-86) on the GPU
+  * ``creatematrix``  ``create_matrix`` with the reference's signature (utils/creatematrix.py:52) — sparse Schur assembly of Q / Abar
+  * ``xm2``       the XM^2 outer loop of the pipeline scripts (3_test_colmap_glomap.py:280-350): residuals, outlier cut, graph clean-up
   * ``binio``     the ``.bin`` wire format (utils/io.py:17-58)
   * ``problems``  synthetic Q generators for the BASELINE configs (no reference code involved)
 
@@ -13,4 +15,4 @@ same three functions from C++ for the reference's demo scripts.  Nothing in this
 """
 from . import binio  # noqa: F401
 
-__all__ = ["binio", "capi", "dist", "recover", "problems"]
+__all__ = ["binio", "capi", "dist", "recover", "creatematrix", "xm2", "problems"]
