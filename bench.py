@@ -15,7 +15,7 @@ XM_BENCH_CAMERAS=<n> changes the camera count (e.g. 13682 = BAL-Final-sized dens
   e2e   : through the C-ABI with HOST buffers — xm_set_q_dense (pinned H2D of Q + re-layout) + xm_trust_region
           (H2D of R0/s0, solve, D2H of R/s) inside the timed region
   roofline      : the dense Q.Y kernel timed alone (xm_bench_qy), algorithmic bytes 72 N^2 + 48 N r
-  cpu_baseline  : the NumPy oracle (port) on the host cores, bounded sample
+  cpu_baseline  : the compiled C + OpenMP oracle (port; oracle/xm_oracle_c.c) on all host cores, bounded sample
   --impl reference : the UNMODIFIED reference trustregion.h (oracle/_ref/xm_ref_harness, cuBLAS path) on the same
           Q on the same GPU — the reference has no CPU implementation of this path; falls back to the oracle port
           on the host when the harness or a GPU is missing.
