@@ -161,6 +161,7 @@ class Handle:
         if rc != 0:
             raise XmError(f"xm_create failed: {ERRORS.get(rc, rc)} (an sm_100 GPU is required; no CPU fallback)")
         self.N = 0
+        self.is_bsr = False
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -213,6 +214,7 @@ class Handle:
         nrows, n3 = Q_slab.shape
         self._check(self.lib.xm_set_q_dense_slab(self._h, n3, row0, nrows, _ptr(Q_slab), nrows), "xm_set_q_dense_slab")
         self.N = n3 // 3
+        self.is_bsr = False
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.xm_set_stream(self._h, C.c_void_p(cuda_stream)), "xm_set_stream")
@@ -223,14 +225,17 @@ class Handle:
         n3 = Q.shape[0]
         self._check(self.lib.xm_set_q_dense(self._h, n3, _ptr(Q), n3), "xm_set_q_dense")
         self.N = n3 // 3
+        self.is_bsr = False
 
     def set_q_dense_ptr(self, n3: int, host_ptr: int, ld: int | None = None):
         self._check(self.lib.xm_set_q_dense(self._h, n3, C.c_void_p(host_ptr), ld or n3), "xm_set_q_dense")
         self.N = n3 // 3
+        self.is_bsr = False
 
     def set_q_dense_dev(self, n3: int, dev_ptr: int, ld: int | None = None):
         self._check(self.lib.xm_set_q_dense_dev(self._h, n3, C.c_void_p(dev_ptr), ld or n3), "xm_set_q_dense_dev")
         self.N = n3 // 3
+        self.is_bsr = False
 
     def set_q_bsr(self, rowptr, colidx, vals, bdim: int):
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
@@ -239,6 +244,7 @@ class Handle:
         nb = rowptr.size - 1
         self._check(self.lib.xm_set_q_bsr(self._h, nb, bdim, _ptr(rowptr), _ptr(colidx), _ptr(vals)), "xm_set_q_bsr")
         self.N = nb
+        self.is_bsr = True
 
     # ---- ops
     def qy(self, X, alpha: float = 1.0):
