@@ -239,3 +239,23 @@ def test_certify_is_refused_on_a_communicator(team_factory):
     t.call("set_q_dense", Q)
     with pytest.raises(capi.XmError):
         t.handles[0].certify(xo.from_blocks(Y), s, 0.0, 1.0)
+
+
+def test_python_staircase_on_a_communicator(team_factory):
+    """solver.solve_arrays with the matrix-free certificate on a communicator (one process per GPU only: SciPy serialises
+    ARPACK calls inside a process with a lock held across the operator callbacks, so two ranks in ONE process would wait
+    for each other's collective forever)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        pytest.skip("torchrun only")
+    from xm_code_b200 import solver
+    rng = np.random.default_rng(11)
+    N = 30
+    A = rng.standard_normal((3 * N, 3 * N + 2))
+    Q = A @ A.T / (3 * N)
+    ref = xo.solve(Q, 5, 1e-7, 0.0)
+    t = team_factory(N, 5)
+    t.call("set_q_dense", Q)
+    out = solver.solve_arrays(t.handles[0], 5, 1e-7, 0.0)
+    assert out["certificate_method"] == "lanczos"
+    assert out["rank"] == ref["rank"] and out["status"] == ref["status"]
+    assert abs(out["trace"][-1].primal - ref["trace"][-1].primal) <= 1e-5 * abs(ref["trace"][-1].primal)
