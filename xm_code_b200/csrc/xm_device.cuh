@@ -129,11 +129,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 
 // ---- mbarrier / TMA primitives (PTX; SASS: SYNCS.*, UTMALDG)
