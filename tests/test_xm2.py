@@ -124,3 +124,47 @@ def test_xm2_refine_removes_planted_outliers(tmp_path, gpu_handle_factory):
         c = (np.trace(Rb[fm[i]].T @ rel) - 1.0) / 2.0
         err.append(np.degrees(np.arccos(np.clip(c, -1.0, 1.0))))
     assert np.median(err) < 1.0, np.median(err)
+
+
+def test_refine_host_logic_with_oracle_standins(tmp_path, monkeypatch):
+    """CPU: the control flow of xm2.refine (graph clean-up, assembly, two solves, residual cut, index bookkeeping) with the
+    oracle standing in for the three device calls (solver, recover_XM, residuals)."""
+    from xm_code_b200 import binio, recover as recmod
+
+    class OracleXM:
+        @staticmethod
+        def solve(path, max_rank, tol, lam, max_time):
+            r = xo.solve(binio.load_matrix_from_bin(path + "/Q.bin"), max_rank, tol, lam)
+            binio.save_matrix_to_bin(path + "/R.bin", r["R"]); binio.save_matrix_to_bin(path + "/s.bin", r["s"])
+
+        @staticmethod
+        def solve_rank3(path, max_rank, tol, lam, max_time):
+            r = xo.solve(binio.load_matrix_from_bin(path + "/Q.bin"), 3, tol, lam, rank3_only=True)
+            binio.save_matrix_to_bin(path + "/R.bin", r["R"]); binio.save_matrix_to_bin(path + "/s.bin", r["s"])
+
+    def oracle_recover(Q, R, s, Abar, lam, handle=None):
+        o = xo.recover(R, np.asarray(s).reshape(-1), Abar)
+        return o["R"], o["s"], o["p"], o["t"]
+
+    monkeypatch.setattr(recmod, "recover_XM", oracle_recover)
+    monkeypatch.setattr(xm2, "observation_errors", lambda e, l, w, R, s, t, p, handle=None: xo.observation_errors(e, l, w, R, s, t, p))
+    prob = problems.synthetic_sfm(30, n_landmarks=260, obs_per_camera=60, seed=9)
+    N, M = prob["N"], prob["M"]
+    rng = np.random.default_rng(1)
+    pts = prob["pt"].copy()
+    bad = rng.choice(pts.shape[0], size=pts.shape[0] // 25, replace=False)
+    pts[bad] += 0.5 * rng.standard_normal((bad.size, 3))
+    edges = np.stack([prob["cam"] + 1, prob["lm"] + 1], axis=1)
+    rgbs = np.arange(edges.shape[0])[:, None].repeat(3, axis=1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = xm2.refine(edges, pts, prob["w"], rgbs, N, M, str(tmp_path), solver=OracleXM)
+    kept = set(out["rgbs"][:, 0].tolist())
+    assert len(kept) <= 0.91 * edges.shape[0]
+    assert sum(int(b) in kept for b in bad) <= 0.15 * bad.size
+    assert np.count_nonzero(out["frame_map"] < 0) == 0
+    fm = out["frame_map"]
+    Rb = out["R"].reshape(3, -1, 3).transpose(1, 0, 2)
+    G = prob["R"]
+    anchor = int(np.flatnonzero(fm == 0)[0])
+    err = [np.degrees(np.arccos(np.clip((np.trace(Rb[fm[i]].T @ (G[anchor].T @ G[i])) - 1.0) / 2.0, -1.0, 1.0))) for i in range(N)]
+    assert np.median(err) < 1.0
