@@ -94,3 +94,37 @@ def test_handle_exchange_and_sharding_over_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_rcm_reorder_makes_the_contiguous_partition_a_graph_cut():
+    """A banded view graph whose cameras arrive shuffled: after the RCM reorder the contiguous ranges need only a thin halo;
+    an Erdos-Renyi graph needs (nearly) everything whatever the order.  The permuted operator is the same operator."""
+    from xm_code_b200 import problems
+    rng = np.random.default_rng(0)
+    N = 600
+    # band: camera i sees i-4..i+4, then a random relabelling hides the band
+    rows = np.repeat(np.arange(N), 9); cols = (rows + np.tile(np.arange(-4, 5), N))
+    ok = (cols >= 0) & (cols < N)
+    rows, cols = rows[ok], cols[ok]
+    relabel = rng.permutation(N)
+    r2, c2 = relabel[rows], relabel[cols]
+    order = np.lexsort((c2, r2)); r2, c2 = r2[order], c2[order]
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(r2, minlength=N))]).astype(np.int32)
+    col = c2.astype(np.int32)
+    vals = rng.standard_normal((col.size, 3, 3))
+    before = xdist.halo_statistics(rowptr, col, world=4, ctas_per_rank=10)
+    perm = xdist.rcm_camera_order(rowptr, col)
+    assert sorted(perm.tolist()) == list(range(N))
+    rp2, col2, vals2 = xdist.permute_bsr(rowptr, col, vals, perm)
+    after = xdist.halo_statistics(rp2, col2, world=4, ctas_per_rank=10)
+    assert max(h["halo_fraction"] for h in before) > 0.5
+    assert max(h["halo"] for h in after) <= 16 and max(h["halo_fraction"] for h in after) < 0.05
+    # same operator: (P Q P^T)(P x) = P (Q x)
+    Q = problems.bsr_to_dense(rowptr, col, np.ascontiguousarray(np.swapaxes(vals, 1, 2)))
+    Q2 = problems.bsr_to_dense(rp2, col2, np.ascontiguousarray(np.swapaxes(vals2, 1, 2)))
+    idx = (3 * perm[:, None] + np.arange(3)[None, :]).ravel()
+    np.testing.assert_array_equal(Q2, Q[np.ix_(idx, idx)])
+    # Erdos-Renyi: no cut to find
+    rp, cc, vv = problems.erdos_renyi_bsr(2000, avg_degree=40, seed=1)
+    er = xdist.halo_statistics(*xdist.permute_bsr(rp, cc, vv, xdist.rcm_camera_order(rp, cc))[:2], world=8, ctas_per_rank=10)
+    assert min(h["halo_fraction"] for h in er) > 0.9

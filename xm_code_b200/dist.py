@@ -80,3 +80,48 @@ def detach(handle: "capi.Handle", group=None):
     handle.comm_disconnect()
     dist.barrier(group)
     handle.close()
+
+
+# ------------------------------------------------------------------------------------------------ graph-cut partition (block-CSR)
+def rcm_camera_order(rowptr, colidx):
+    """Reverse Cuthill-McKee order of the cameras of a block-CSR view graph ("simple BFS/RCM bands"): cameras
+    that see each other end up close together, so the library's contiguous camera ranges become a band partition with few
+    boundary cameras.  Returns perm with perm[new] = old."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    rowptr = np.asarray(rowptr); colidx = np.asarray(colidx)
+    n = rowptr.size - 1
+    g = sp.csr_matrix((np.ones(colidx.size, dtype=np.int8), colidx, rowptr), shape=(n, n))
+    return np.asarray(reverse_cuthill_mckee(g, symmetric_mode=True), dtype=np.int64)
+
+
+def permute_bsr(rowptr, colidx, vals, perm):
+    """Symmetric permutation P Q P^T of a block-CSR matrix: new camera k is old camera perm[k].  Block values are carried
+    along unchanged (rows and columns of a 3x3 block belong to one camera each)."""
+    rowptr = np.asarray(rowptr); colidx = np.asarray(colidx); vals = np.asarray(vals)
+    n = rowptr.size - 1
+    inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+    counts = np.diff(rowptr)[perm]
+    new_rowptr = np.concatenate([[0], np.cumsum(counts)]).astype(rowptr.dtype)
+    src = np.concatenate([np.arange(rowptr[o], rowptr[o + 1]) for o in perm]) if n else np.zeros(0, dtype=np.int64)
+    new_col = inv[colidx[src]]
+    # sort every row by its new column index (the library does not need it, CSR consumers usually expect it)
+    row_of = np.repeat(np.arange(n), counts)
+    order = np.lexsort((new_col, row_of))
+    return new_rowptr, new_col[order].astype(colidx.dtype), vals[src][order]
+
+
+def halo_statistics(rowptr, colidx, world: int, ctas_per_rank: int = 148):
+    """For the library's contiguous camera partition: per rank, how many cameras it owns, how many REMOTE cameras its block
+    rows reference (the halo a boundary-only exchange would have to fetch) and the fraction of all remote cameras that is —
+    1.0 means the full all-gather the kernels do today is already minimal (Erdos-Renyi), << 1 means a boundary-only exchange
+    would move that much less (banded view graphs after rcm_camera_order)."""
+    rowptr = np.asarray(rowptr); colidx = np.asarray(colidx)
+    n = rowptr.size - 1
+    out = []
+    for k, (lo, hi) in enumerate(partition_table(n, world, ctas_per_rank)):
+        cols = np.unique(colidx[rowptr[lo]:rowptr[hi]])
+        remote = cols[(cols < lo) | (cols >= hi)]
+        out.append(dict(rank=k, cameras=hi - lo, halo=int(remote.size), remote_total=n - (hi - lo),
+                        halo_fraction=float(remote.size) / max(1, n - (hi - lo))))
+    return out
