@@ -1,20 +1,21 @@
-// xm_inst.cu — instantiations of the persistent solve kernel and the op-level kernel for one group of padded ranks.
-// Compiled three times (-DXM_INST_GROUP=0/1/2) so the build runs in parallel; see xm_capi.cu:launch_any.
+// xm_inst.cu — instantiations of the persistent solve kernel and the op-level kernel for one group of padded ranks and ONE
+// Q.Y path.  Compiled nine times (-DXM_INST_GROUP=0/1/2 x -DXM_INST_PATH=0/1/2) so the build runs in parallel; see
+// xm_capi.cu:launch_any.  PATH: 0 = dense through the TMA ring, 1 = dense by direct loads, 2 = block-CSR.
 #include "xm_host.h"
 #include "xm_solve.cuh"
 
 using namespace xm;
 
-#ifndef XM_INST_GROUP
-#error "compile with -DXM_INST_GROUP=0|1|2"
+#if !defined(XM_INST_GROUP) || !defined(XM_INST_PATH)
+#error "compile with -DXM_INST_GROUP=0|1|2 -DXM_INST_PATH=0|1|2"
 #endif
+constexpr int kPath = XM_INST_PATH;
+#define XM_CAT_(g, p) xm_launch_group##g##_path##p
+#define XM_GROUP_FN(g, p) XM_CAT_(g, p)        // two levels: XM_INST_PATH is expanded before it is pasted
 
 template <int RP, int NT>
 static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
-    const void* fn;
-    // PATH: 0 = dense through the TMA ring, 1 = dense by direct loads, 2 = block-CSR
-    if (kind == 0) fn = d.use_tma ? (const void*)xm_solve_kernel<RP, NT, 0> : d.Q ? (const void*)xm_solve_kernel<RP, NT, 1> : (const void*)xm_solve_kernel<RP, NT, 2>;
-    else           fn = d.use_tma ? (const void*)xm_ops_kernel<RP, NT, 0> : d.Q ? (const void*)xm_ops_kernel<RP, NT, 1> : (const void*)xm_ops_kernel<RP, NT, 2>;
+    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, NT, kPath> : (const void*)xm_ops_kernel<RP, NT, kPath>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     if (kind == 0) {
@@ -28,7 +29,7 @@ static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opco
 // block-CSR kernels hold 3 accumulators per lane whatever the rank: 512 threads for every RP
 template <int RP>
 static cudaError_t launch_bsr(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
-    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, 512, 2> : (const void*)xm_ops_kernel<RP, 512, 2>;
+    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, 512, kPath> : (const void*)xm_ops_kernel<RP, 512, kPath>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     if (kind == 0) {
@@ -40,7 +41,7 @@ static cudaError_t launch_bsr(int kind, const xm_handle* h, const Dev& d, int op
 }
 
 #if XM_INST_GROUP == 0
-cudaError_t xm_launch_group0(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+cudaError_t XM_GROUP_FN(0, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
         case 3: return launch_t<3, 512>(kind, h, d, opcode, dyn, st);
         case 4: return launch_t<4, 512>(kind, h, d, opcode, dyn, st);
@@ -49,7 +50,7 @@ cudaError_t xm_launch_group0(int kind, int RP, const xm_handle* h, const Dev& d,
     return cudaErrorInvalidValue;
 }
 #elif XM_INST_GROUP == 1
-cudaError_t xm_launch_group1(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+cudaError_t XM_GROUP_FN(1, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
         case 6: return launch_t<6, 512>(kind, h, d, opcode, dyn, st);
         case 8: return launch_t<8, 512>(kind, h, d, opcode, dyn, st);
@@ -58,11 +59,17 @@ cudaError_t xm_launch_group1(int kind, int RP, const xm_handle* h, const Dev& d,
     return cudaErrorInvalidValue;
 }
 #else
-cudaError_t xm_launch_group2(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+cudaError_t XM_GROUP_FN(2, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
-        case 12: return d.bsr_val ? launch_bsr<12>(kind, h, d, opcode, dyn, st) : launch_t<12, 256>(kind, h, d, opcode, dyn, st);
-        case 16: return d.bsr_val ? launch_bsr<16>(kind, h, d, opcode, dyn, st) : launch_t<16, 256>(kind, h, d, opcode, dyn, st);
-        case 20: return d.bsr_val ? launch_bsr<20>(kind, h, d, opcode, dyn, st) : launch_t<20, 256>(kind, h, d, opcode, dyn, st);
+#if XM_INST_PATH == 2
+        case 12: return launch_bsr<12>(kind, h, d, opcode, dyn, st);
+        case 16: return launch_bsr<16>(kind, h, d, opcode, dyn, st);
+        case 20: return launch_bsr<20>(kind, h, d, opcode, dyn, st);
+#else
+        case 12: return launch_t<12, 256>(kind, h, d, opcode, dyn, st);
+        case 16: return launch_t<16, 256>(kind, h, d, opcode, dyn, st);
+        case 20: return launch_t<20, 256>(kind, h, d, opcode, dyn, st);
+#endif
     }
     return cudaErrorInvalidValue;
 }
