@@ -53,6 +53,23 @@ def make_problem():
     return np.asfortranarray(Q), prob
 
 
+BIG = N_CAMERAS >= 4000      # large-problem mode (e.g. XM_BENCH_CAMERAS=13682, BAL-Final-sized: 13.5 GB of Q)
+
+
+def make_problem_shared(world, rank):
+    """Large problems under torchrun: rank 0 assembles Q once (tens of seconds of host BLAS, ~4x the matrix in host memory)
+    and shares it through /dev/shm; every rank maps it read-only and uploads only the rows of its cameras."""
+    import torch.distributed as dist
+    path = f"/dev/shm/xm_bench_Q_{N_CAMERAS}.npy"
+    if rank == 0:
+        Q, _ = make_problem()
+        np.save(path + ".tmp.npy", np.ascontiguousarray(Q))     # symmetric: C order == column-major
+        os.replace(path + ".tmp.npy", path)
+        del Q
+    dist.barrier()
+    return np.load(path, mmap_mode="r")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -136,7 +153,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    Qh, prob = make_problem()
+    big = BIG and world > 1
+    Qh = make_problem_shared(world, rank) if big else make_problem()[0]
     N = N_CAMERAS; n3 = 3 * N
     h = capi.Handle(device=local, profile=bool(int(os.environ.get("XM_PROFILE", "0"))), qy_variant=int(os.environ.get("XM_QY_VARIANT", "0")),
                     vec_in_global=bool(int(os.environ.get("XM_VEC_GLOBAL", "0"))))
@@ -147,7 +165,11 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
     # host (pinned) and device copies of the inputs, wire layout (column-major)
-    Q_pin = torch.from_numpy(Qh.T.copy()).pin_memory()           # memory of the .T copy == column-major Q
+    if big:      # only this rank's row slab is pinned / resident: column-major slab = the transposed rows, leading dimension nrows
+        row0, nrows = 3 * cam_lo, 3 * (cam_hi - cam_lo)
+        Q_pin = torch.from_numpy(np.ascontiguousarray(Qh[row0:row0 + nrows, :].T)).pin_memory()
+    else:
+        Q_pin = torch.from_numpy(Qh.T.copy()).pin_memory()       # memory of the .T copy == column-major Q
     Q_dev = Q_pin.cuda(non_blocking=True)
     R0_np = np.zeros((n3, RANK), order="F")
     for a in range(3):
@@ -163,8 +185,18 @@ def run_ours(args):
                                            lam=LAM, gradtol=GRADTOL)
         return primal, st
 
+    def upload_q(ptr, dev):
+        if big:
+            fn = h.lib.xm_set_q_dense_slab_dev if dev else h.lib.xm_set_q_dense_slab
+            h._check(fn(h._h, n3, row0, nrows, capi.C.c_void_p(ptr), nrows), "xm_set_q_dense_slab")
+            h.N = N
+        elif dev:
+            h.set_q_dense_dev(n3, ptr, n3)
+        else:
+            h.set_q_dense_ptr(n3, ptr, n3)                      # a rank of a communicator copies only its own rows
+
     def step_e2e():
-        h.set_q_dense_ptr(n3, Q_pin.data_ptr(), n3)             # a rank of a communicator copies only its own rows
+        upload_q(Q_pin.data_ptr(), False)
         gt = capi.C.c_double(GRADTOL); pr = capi.C.c_double(); st = capi.XmStats()
         rc = h.lib.xm_trust_region(h._h, RANK, capi.C.c_void_p(R0_pin.data_ptr()), capi.C.c_void_p(s0_pin.data_ptr()), LAM, capi.C.byref(gt),
                                    0.0, None, 1000.0, capi.C.c_void_p(R_out.data_ptr()), capi.C.c_void_p(s_out.data_ptr()),
@@ -196,7 +228,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms, iters, last
 
-    h.set_q_dense_dev(n3, Q_dev.data_ptr(), n3)
+    upload_q(Q_dev.data_ptr(), True)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
