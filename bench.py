@@ -152,7 +152,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the XM hot path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # large-problem mode: the other ranks wait in a barrier while rank 0 assembles Q on the host (minutes at BAL-Final size)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=60 if BIG else 10))
     big = BIG and world > 1
     Qh = make_problem_shared(world, rank) if big else make_problem()[0]
     N = N_CAMERAS; n3 = 3 * N
