@@ -166,12 +166,15 @@ class TRResult:
 
 
 def trust_region(Q, Y0, s0, lam, gradtol, ls_step=0.0, v=None, max_time=1000.0,
-                 replicate_stale_sr=True, verbose=False) -> TRResult:
+                 replicate_stale_sr=True, verbose=False, e_recurrence=False) -> TRResult:
     """Restatement of XMtrustregion (trustregion.h:77-724).
 
     Q: (3N,3N) dense float64.  Y0: (N,3,r).  s0: (N,) with s0[0]==1.  v: (3N,) escape direction when ls_step!=0.
     ``replicate_stale_sr``: quirk Q3 — after an accepted rank-escalation line search the reference keeps the
     stale ``sR`` (old R) for loss[0], the first gradient and the first CsR (trustregion.h:394-398 vs :422,467,553).
+    ``e_recurrence`` (NOT reference behaviour; design study for a tCG iteration with two barriers instead of three,
+    DESIGN.md §8): the Euclidean Hessian product E = 2 Q X(p) is not recomputed from the new direction but updated as
+    E <- beta E - 2 Q X(r_new), X(r) = s r_R + r_s Y — the product's operand then needs only the new residual, not beta.
     """
     t_start = time.perf_counter()
     Q = np.asarray(Q, dtype=np.float64)
@@ -253,8 +256,16 @@ def trust_region(Q, Y0, s0, lam, gradtol, ls_step=0.0, v=None, max_time=1000.0,
         # CsR = 2 Q sR (:553) — same product as D above (same sR); the reference recomputes it.
         nqy += 1
         i = 0
+        E_rec = None
         for i in range(MAX_INNER_ITER):
-            hr, hs = ehess(Q, Y, s, lam, D, pR, ps); nqy += 1
+            if e_recurrence:
+                if E_rec is None:
+                    E_rec = qy(Q, pR * s[:, None, None] + Y * ps[:, None, None], 2.0); nqy += 1
+                hr = E_rec * s[:, None, None] + D * ps[:, None, None]
+                hs = np.einsum("iaj,iaj->i", E_rec, Y) + np.einsum("iaj,iaj->i", D, pR) + 4.0 * lam * (3.0 * s * s - 1.0) * ps
+                hs[0] = 0.0
+            else:
+                hr, hs = ehess(Q, Y, s, lam, D, pR, ps); nqy += 1
             rhr, rhs = ehess2rhess(Y, s, G, g, hr, hs, pR, ps)
             rhsds = np.zeros(N); rhsds[1:] = rhs[1:] / (s[1:] ** 2)
             alpha = rdotr / inner(pR, rhr, ps, rhsds)  # :566
@@ -276,6 +287,8 @@ def trust_region(Q, Y0, s0, lam, gradtol, ls_step=0.0, v=None, max_time=1000.0,
                 endreason = 3
                 break
             beta = rdotr_new / rdotr
+            if e_recurrence:      # the product of this iteration: operand from the NEW RESIDUAL only
+                E_rec = beta * E_rec - qy(Q, rR * s[:, None, None] + Y * rs[:, None, None], 2.0); nqy += 1
             pR = beta * pR - rR
             ps = beta * ps - rs
             vdotv, vdotp, pdotp = (vdotv + 2 * alpha * vdotp + alpha * alpha * pdotp,

@@ -153,3 +153,19 @@ def test_bin_roundtrip(tmp_path):
     M = np.arange(12, dtype=np.float64).reshape(4, 3)
     xo.save_bin(tmp_path / "m.bin", M)
     np.testing.assert_array_equal(xo.load_bin(tmp_path / "m.bin"), M)
+
+
+def test_e_recurrence_design_study_keeps_parity(simple1_q, simple2_q):
+    """Design study for a tCG iteration with two barriers instead of three: updating the Euclidean Hessian
+    product by the recurrence E <- beta E - 2 Q X(r_new) instead of recomputing 2 Q X(p_new) keeps the solver inside the
+    parity bars (objective 1e-10, s 1e-8) and, while the problem is well conditioned, on the same trajectory."""
+    from xm_code_b200 import problems
+    for Q, r, lam, tol in ((simple1_q, 3, 0.0, 1e-16), (simple2_q, 3, 0.0, 1e-10), (problems.synthetic_dense_q(120, seed=5)[0], 5, 0.05, 1e-8)):
+        N = Q.shape[0] // 3
+        a = xo.trust_region(Q, xo.identity_init(N, r), np.ones(N), lam, tol)
+        b = xo.trust_region(Q, xo.identity_init(N, r), np.ones(N), lam, tol, e_recurrence=True)
+        assert abs(a.primal - b.primal) <= 1e-10 * abs(a.primal)
+        np.testing.assert_allclose(a.s, b.s, atol=1e-8)
+        assert a.outer_iters == b.outer_iters and abs(a.tcg_iters - b.tcg_iters) <= 0.02 * a.tcg_iters + 2
+        n = len(a.log) - 3
+        assert all(x[0] == y[0] and x[1] == y[1] and x[4] == y[4] and x[5] == y[5] for x, y in zip(a.log[:n], b.log[:n]))
