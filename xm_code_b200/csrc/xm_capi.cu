@@ -436,6 +436,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.partials = (double*)q;
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
     d.x_cam_major = h->is_bsr ? 1 : 0;
+    d.e_rec = 0;
+    if (const char* e = getenv("XM_TUNE_EREC")) d.e_rec = atoi(e) ? 1 : 0;                        // EXPERIMENT: two-barrier tCG iteration
     d.bsr_stage = 0; d.bsr_k8 = 0;          // measured best on B200 (profiles/r01_bsr_qy.md): bulk-TMA chunks, 4 gathers per sub-warp
     if (const char* e = getenv("XM_TUNE_BSR")) { const int v = atoi(e); d.bsr_stage = v & 1; d.bsr_k8 = (v >> 1) & 1; }      // A/B hook
     d.Q = h->is_bsr ? nullptr : h->Qp;

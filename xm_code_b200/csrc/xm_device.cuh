@@ -27,7 +27,7 @@ constexpr int kBsrChunk = 32;       // block-CSR: blocks per staged chunk (32 x 
 constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node that can share a solve (camera partition, peer-mapped exchange)
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
-enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, kNumVecR };
+enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, V_E, kNumVecR };   // V_E: 2 Q X(p) (e_rec only)
 enum ScaId : int { S_S = 0, S_SNEW, S_GS, S_RGS, S_PS, S_RS, S_VS, S_HVS, S_HPS, kNumVecS };
 
 struct LogRec { int k, inner_shown, trstatus, endreason; double loss, gradnorm, delta; };
@@ -86,6 +86,9 @@ struct Dev {
     double *S6;                // N*6 : sym(Y_i EG_i^T), order 00 01 02 11 12 22
     int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
     int profile;               // fine-grained phase timers on (costs a few percent)
+    int e_rec;                 // EXPERIMENT (XM_TUNE_EREC): two-barrier tCG iteration — E = 2QX(p) kept by the recurrence
+                               // E <- beta E - 2 Q X(r_new); the product's operand is built from the new residual in the update
+                               // phase and rides on the <r,r> reduction barrier (oracle study: tests/test_oracle.py)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
     int bsr_stage, bsr_k8;     // block-CSR staging: 0 = one bulk-TMA copy per chunk, 1 = cp.async; gathers in flight per sub-warp: 4 or 8
     int x_cam_major;           // operand layout: 0 = j-major Xt[j*ldq + row] (dense paths, TMA boxes), 1 = camera-major Xt[row*r + j]
@@ -238,6 +241,7 @@ struct Ctx {
     double* ring; unsigned long long *fullQ, *fullX, *empty;
     double* bsr_buf; unsigned long long* bsr_bar; unsigned bsr_phase;   // block-CSR: this warp's two staged chunks, their mbarriers, parity bits
     unsigned g_use; int prefetched;
+    double erec_beta; bool erec_first;   // e_rec: beta of the pending direction update; first product of a tCG solve
     double* red;                // smem [NWARPS][3][RP]
     double* bsum;               // smem [NWARPS]
     double* bcast;              // smem [4]
@@ -261,6 +265,7 @@ struct Ctx {
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
         ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
+        erec_beta = 0.0; erec_first = true;
         bsr_buf = nullptr; bsr_bar = nullptr; bsr_phase = 0;
     }
     // end of a launch: remember the epoch for the next one (every CTA has long read epoch_store by now: it sits behind at
@@ -729,13 +734,33 @@ __device__ __forceinline__ double epi_hess(Ctx<RP, NT, MG>& c, int i, const doub
     const bool act = c.act && valid;
     double y[3], p[3], dd[3];
     ld3(c.R(c.iY), i, r, c.j, act, y); ld3(c.R(V_P), i, r, c.j, act, p); ld3(c.R(c.iD), i, r, c.j, act, dd);
-    const double si = c.S(c.iS)[i], psi = c.S(S_PS)[i], gi = c.S(S_GS)[i];
+    const double si = c.S(c.iS)[i], gi = c.S(S_GS)[i];
+    double psi = c.S(S_PS)[i];
     double S[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) S[q] = c.s6[(size_t)i * 6 + q];
     double e[3], hr[3], t[3], sp[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { e[a] = 2.0 * E[a]; hr[a] = si * e[a] + psi * dd[a]; }
+    for (int a = 0; a < 3; ++a) e[a] = 2.0 * E[a];
+    if (d.e_rec) {
+        // two-barrier iteration: the product just computed is 2 Q X(r_new) (2 Q X(p_0) for the first product of a tCG solve).
+        // Finish the direction update here (trustregion.h:634-638: p = beta p - r) and keep E = 2 Q X(p) by its recurrence.
+        if (!c.erec_first) {
+            const double beta = c.erec_beta;
+            double rr[3], ep[3];
+            ld3(c.R(V_RR), i, r, c.j, act, rr); ld3(c.R(V_E), i, r, c.j, act, ep);
+            const double rsi = c.S(S_RS)[i];
+            __syncwarp();                                   // every lane of the sub-warp has read S_PS[i] before lane 0 rewrites it
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { p[a] = beta * p[a] - rr[a]; e[a] = beta * ep[a] - e[a]; }
+            psi = (i > 0) ? beta * psi - rsi : 0.0;
+            st3(c.R(V_P), i, r, c.j, act, p);
+            if (c.j == 0 && valid) c.S(S_PS)[i] = psi;
+        }
+        st3(c.R(V_E), i, r, c.j, act, e);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) hr[a] = si * e[a] + psi * dd[a];
     symv(S, p, sp);
 #pragma unroll
     for (int a = 0; a < 3; ++a) t[a] = hr[a] - sp[a];

@@ -136,6 +136,7 @@ __device__ __forceinline__ double phase_update(Ctx<RP, NT, MG>& c, double alpha)
     const Dev& d = c.d;
     const int r = d.r;
     double part = 0.0;
+    if (d.e_rec) c.begin_push();                // e_rec: this phase also builds the next product's operand X(r_new) = s r_R + r_s Y
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -146,14 +147,24 @@ __device__ __forceinline__ double phase_update(Ctx<RP, NT, MG>& c, double alpha)
         for (int a = 0; a < 3; ++a) { v[a] += alpha * p[a]; rr[a] += alpha * hp[a]; hv[a] += alpha * hp[a]; }
         st3(c.R(V_V), i, r, c.j, act, v); st3(c.R(V_RR), i, r, c.j, act, rr); st3(c.R(V_HV), i, r, c.j, act, hv);
         if (act) part += rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2];
+        // every lane of the sub-warp computes the new scale residual (lane 0 stores it): the e_rec operand needs it in all lanes
+        double rsi = 0.0;
+        if (valid && i > 0) rsi = c.S(S_RS)[i] + alpha * c.S(S_HPS)[i];
+        __syncwarp();
         if (valid && c.j == 0 && i > 0) {
             const double psi = c.S(S_PS)[i], hpsi = c.S(S_HPS)[i];
             c.S(S_VS)[i] += alpha * psi;
-            const double rsi = c.S(S_RS)[i] + alpha * hpsi;
             c.S(S_RS)[i] = rsi;
             c.S(S_HVS)[i] += alpha * hpsi;
             const double t = rsi / c.S(c.iS)[i];
             part += t * t;
+        }
+        if (d.e_rec) {
+            double y[3];
+            ld3(c.R(c.iY), i, r, c.j, act, y);
+            const double si = valid ? c.S(c.iS)[i] : 0.0;
+            const double x[3] = {si * rr[0] + rsi * y[0], si * rr[1] + rsi * y[1], si * rr[2] + rsi * y[2]};
+            st_operand(c, i, act, x);
         }
     }
     return part;
@@ -324,11 +335,13 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
         endreason = 6; trstatus = 4;
         double vdotv = 0.0, vdotp = 0.0, pdotp = rdotr;
 
+        c.erec_first = true;
         for (i_inner = 0; i_inner < d.max_inner; ++i_inner) {                       // :559-664
             ObjArgs oa{nullptr, nullptr, nullptr};
             c.trace_on = (d.profile && lead && nqy >= 200 && nqy < 202);
             c.tr(1);
             const double ph = qy_phase<RP, NT, MODE_HESS, PATH>(c, oa, mapsQ.m, &mapX);
+            c.erec_first = false;
             c.tr(2);
             c.publish(ph); XM_GSYNC(c);
             c.tr(3);
@@ -346,15 +359,24 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
             c.tr(4);
             const double pr = phase_update(c, alpha);
             c.tr(5);
-            c.publish(pr); XM_GSYNC(c);
+            if (d.e_rec) {                          // the operand X(r_new) rides on the <r,r> reduction barrier: two barriers per iteration
+                c.unpack_operand();
+                c.publish(pr); XM_GSYNC_PUSHED(c);
+            } else {
+                c.publish(pr); XM_GSYNC(c);
+            }
             c.tr(6);
             const double rdotr_new = c.collect();                                   // :626
             if (sqrt(rdotr_new) < gradnorm * fmin(gradnorm, 0.1)) { endreason = 3; break; }   // :627-630
             const double beta = rdotr_new / rdotr;
             c.tr(7);
-            phase_dir(c, beta);
-            c.tr(8);
-            XM_OSYNC(c);
+            if (d.e_rec) {
+                c.erec_beta = beta;                 // p = beta p - r and E = beta E - 2 Q X(r) happen in the next product's epilogue
+            } else {
+                phase_dir(c, beta);
+                c.tr(8);
+                XM_OSYNC(c);
+            }
             c.tr(9);
             const double nvv = vdotv + 2 * alpha * vdotp + alpha * alpha * pdotp;   // :642-644
             const double nvp = beta * (vdotp + alpha * pdotp);
