@@ -189,3 +189,20 @@ def test_simple2_pipeline_end_to_end(tmp_path, simple2_obs, gpu_handle_factory):
     ref = xo.recover(R, s[:, 0], Abar)
     np.testing.assert_allclose(R_real, ref["R"], atol=1e-10)
     np.testing.assert_allclose(t_est, ref["t"], atol=1e-8 * max(1.0, np.abs(ref["t"]).max()))
+
+
+@pytest.mark.parametrize("erec", ["1"])
+def test_two_barrier_iteration_keeps_parity(gpu_handle_factory, simple1_q, simple2_q, erec, monkeypatch):
+    """EXPERIMENT (branch tcg2): XM_TUNE_EREC=1 — E = 2QX(p) by recurrence, operand from the new residual, two barriers per
+    tCG iteration.  Same parity bars as the standard iteration (oracle study: tests/test_oracle.py)."""
+    monkeypatch.setenv("XM_TUNE_EREC", erec)
+    from xm_code_b200 import problems
+    for Q, r, lam, tol in ((simple1_q, 3, 0.0, 1e-16), (simple2_q, 3, 0.0, 1e-10), (problems.synthetic_dense_q(120, seed=5)[0], 5, 0.05, 1e-8)):
+        N = Q.shape[0] // 3
+        h = gpu_handle_factory()
+        h.set_q_dense(Q)
+        Y0 = xo.identity_init(N, r)
+        got = h.trust_region(xo.from_blocks(Y0), np.ones(N), lam, tol)
+        ref = xo.trust_region(Q, Y0, np.ones(N), lam, tol)
+        check_point(got, ref, primal_rel=1e-9, s_abs=1e-7, x_abs=1e-6)
+        assert got.stats["outer_iters"] == ref.outer_iters

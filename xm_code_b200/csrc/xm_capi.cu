@@ -436,6 +436,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.partials = (double*)q;
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
     d.x_cam_major = h->is_bsr ? 1 : 0;
+    d.e_rec = 0;
+    if (const char* e = getenv("XM_TUNE_EREC")) d.e_rec = atoi(e) ? 1 : 0;                        // EXPERIMENT: two-barrier tCG iteration
     d.bsr_stage = 0; d.bsr_k8 = 0;          // measured best on B200 (profiles/r01_bsr_qy.md): bulk-TMA chunks, 4 gathers per sub-warp
     if (const char* e = getenv("XM_TUNE_BSR")) { const int v = atoi(e); d.bsr_stage = v & 1; d.bsr_k8 = (v >> 1) & 1; }      // A/B hook
     d.Q = h->is_bsr ? nullptr : h->Qp;
@@ -500,20 +502,26 @@ static int ensure_io(xm_handle* h, int r) {
     return XM_OK;
 }
 
-// Kernel instantiations live in xm_inst.cu, compiled nine times (groups of padded ranks x Q.Y path) so the build parallelises.
-#define XM_DECL(g, p) cudaError_t xm_launch_group##g##_path##p(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st);
-XM_DECL(0, 0) XM_DECL(1, 0) XM_DECL(2, 0) XM_DECL(0, 1) XM_DECL(1, 1) XM_DECL(2, 1) XM_DECL(0, 2) XM_DECL(1, 2) XM_DECL(2, 2)
+// Kernel instantiations live in xm_inst.cu, compiled 18 times (groups of padded ranks x Q.Y path x one-GPU / communicator
+// build) so the build parallelises.
+#define XM_DECL(g, p, m) cudaError_t xm_launch_group##g##_path##p##_mg##m(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st);
+#define XM_DECL3(g, m) XM_DECL(g, 0, m) XM_DECL(g, 1, m) XM_DECL(g, 2, m)
+XM_DECL3(0, 0) XM_DECL3(1, 0) XM_DECL3(2, 0) XM_DECL3(0, 1) XM_DECL3(1, 1) XM_DECL3(2, 1)
+#undef XM_DECL3
 #undef XM_DECL
 
 static cudaError_t launch_any(int kind, const xm_handle* h, const Dev& d, int opcode, const Plan& p, cudaStream_t st) {
     typedef cudaError_t (*Fn)(int, int, const xm_handle*, const Dev&, int, size_t, cudaStream_t);
-    static const Fn table[3][3] = {      // [rank group: RP 3,4,5 / 6,8,10 / 12,16,20][path: TMA ring / dense direct / block-CSR]
-        {xm_launch_group0_path0, xm_launch_group0_path1, xm_launch_group0_path2},
-        {xm_launch_group1_path0, xm_launch_group1_path1, xm_launch_group1_path2},
-        {xm_launch_group2_path0, xm_launch_group2_path1, xm_launch_group2_path2}};
+    static const Fn table[2][3][3] = {   // [communicator?][rank group: RP 3,4,5 / 6,8,10 / 12,16,20][path: TMA ring / dense direct / block-CSR]
+        {{xm_launch_group0_path0_mg0, xm_launch_group0_path1_mg0, xm_launch_group0_path2_mg0},
+         {xm_launch_group1_path0_mg0, xm_launch_group1_path1_mg0, xm_launch_group1_path2_mg0},
+         {xm_launch_group2_path0_mg0, xm_launch_group2_path1_mg0, xm_launch_group2_path2_mg0}},
+        {{xm_launch_group0_path0_mg1, xm_launch_group0_path1_mg1, xm_launch_group0_path2_mg1},
+         {xm_launch_group1_path0_mg1, xm_launch_group1_path1_mg1, xm_launch_group1_path2_mg1},
+         {xm_launch_group2_path0_mg1, xm_launch_group2_path1_mg1, xm_launch_group2_path2_mg1}}};
     const int g = (p.RP <= 5) ? 0 : (p.RP <= 10) ? 1 : 2;
     const int path = d.use_tma ? 0 : (d.Q ? 1 : 2);
-    return table[g][path](kind, p.RP, h, d, opcode, p.dyn_smem, st);
+    return table[d.world > 1 ? 1 : 0][g][path](kind, p.RP, h, d, opcode, p.dyn_smem, st);
 }
 static cudaError_t launch_solve(const xm_handle* h, const Dev& d, const Plan& p, cudaStream_t st) { return launch_any(0, h, d, 0, p, st); }
 static cudaError_t launch_ops(const xm_handle* h, const Dev& d, int opcode, const Plan& p, cudaStream_t st) { return launch_any(1, h, d, opcode, p, st); }

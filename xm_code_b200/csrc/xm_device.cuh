@@ -27,7 +27,7 @@ constexpr int kBsrChunk = 32;       // block-CSR: blocks per staged chunk (32 x 
 constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node that can share a solve (camera partition, peer-mapped exchange)
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
-enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, kNumVecR };
+enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, V_E, kNumVecR };   // V_E: 2 Q X(p) (e_rec only)
 enum ScaId : int { S_S = 0, S_SNEW, S_GS, S_RGS, S_PS, S_RS, S_VS, S_HVS, S_HPS, kNumVecS };
 
 struct LogRec { int k, inner_shown, trstatus, endreason; double loss, gradnorm, delta; };
@@ -86,6 +86,9 @@ struct Dev {
     double *S6;                // N*6 : sym(Y_i EG_i^T), order 00 01 02 11 12 22
     int vec_smem, cpc_max;     // per-CTA state in shared memory; max cameras per CTA
     int profile;               // fine-grained phase timers on (costs a few percent)
+    int e_rec;                 // EXPERIMENT (XM_TUNE_EREC): two-barrier tCG iteration — E = 2QX(p) kept by the recurrence
+                               // E <- beta E - 2 Q X(r_new); the product's operand is built from the new residual in the update
+                               // phase and rides on the <r,r> reduction barrier (oracle study: tests/test_oracle.py)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
     int bsr_stage, bsr_k8;     // block-CSR staging: 0 = one bulk-TMA copy per chunk, 1 = cp.async; gathers in flight per sub-warp: 4 or 8
     int x_cam_major;           // operand layout: 0 = j-major Xt[j*ldq + row] (dense paths, TMA boxes), 1 = camera-major Xt[row*r + j]
@@ -206,8 +209,10 @@ __device__ __forceinline__ double warpsum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------ per-thread context
-template <int RP, int NT>
+template <int RP, int NT, bool MG = true>
 struct Ctx {
+    // MG = false: instantiation for one GPU only — every multi-GPU branch below folds away at compile time
+    __device__ __forceinline__ int world() const { return MG ? d.world : 1; }
     static constexpr int NWARPS = NT / 32;
     const Dev& d;
     int tid, lane, warp, W, cpw, sw, j, slot, NSW;
@@ -236,6 +241,7 @@ struct Ctx {
     double* ring; unsigned long long *fullQ, *fullX, *empty;
     double* bsr_buf; unsigned long long* bsr_bar; unsigned bsr_phase;   // block-CSR: this warp's two staged chunks, their mbarriers, parity bits
     unsigned g_use; int prefetched;
+    double erec_beta; bool erec_first;   // e_rec: beta of the pending direction update; first product of a tCG solve
     double* red;                // smem [NWARPS][3][RP]
     double* bsum;               // smem [NWARPS]
     double* bcast;              // smem [4]
@@ -259,6 +265,7 @@ struct Ctx {
         rbase = d.rbase; rstride = d.rstride; sbase = d.sbase; sstride = d.sstride; s6 = d.S6;
         iY = V_Y; iYn = V_YNEW; iD = V_D; iDn = V_DNEW; iS = S_S; iSn = S_SNEW;
         ring = nullptr; fullQ = fullX = empty = nullptr; g_use = 0; prefetched = 0;
+        erec_beta = 0.0; erec_first = true;
         bsr_buf = nullptr; bsr_bar = nullptr; bsr_phase = 0;
     }
     // end of a launch: remember the epoch for the next one (every CTA has long read epoch_store by now: it sits behind at
@@ -301,14 +308,14 @@ struct Ctx {
         }
     }
     __device__ __forceinline__ void raise_abort() {
-        for (int w = 0; w < d.world; ++w) *(volatile int*)d.abort_peer[w] = 1;
+        for (int w = 0; w < world(); ++w) *(volatile int*)d.abort_peer[w] = 1;
     }
     // bounded spin helper: false = give up (abort flag seen or watchdog fired)
     __device__ __forceinline__ bool spin_ok(unsigned& spins, unsigned long long t0) {
         if ((++spins & 0x3ffu) != 0) return true;
         if (*(volatile int*)d.abort_flag) return false;
         // multi-GPU: generous — the ranks' hosts launch independently (a peer may reach its launch seconds later)
-        if (gtimer() - t0 > (d.world > 1 ? 30000000000ull : 4000000000ull)) { raise_abort(); return false; }
+        if (gtimer() - t0 > (world() > 1 ? 30000000000ull : 4000000000ull)) { raise_abort(); return false; }
         return true;
     }
     // warp 0: fixed-order sum of the first `n` slots; the flag sits in slot n.  Every lane returns the totals.
@@ -376,7 +383,7 @@ struct Ctx {
             if (d.profile) { const unsigned long long t = gtimer(); bseg[0] += t - t0; tseg = t; }
         }
         __syncwarp();
-        const int nw = 4 * d.world;                                              // 4 words per message: sum lo/hi, flag lo/hi
+        const int nw = 4 * world();                                              // 4 words per message: sum lo/hi, flag lo/hi
         unsigned long long* inbox = d.ll + (size_t)pbuf * (4 * kMaxWorld);
         if (blockIdx.x == 0) {                                                   // leader: gather the rank's slots as they arrive
             constexpr int MAXS = 5;
@@ -425,7 +432,7 @@ struct Ctx {
         if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[4] += t - tseg; }
         const unsigned lo32 = (unsigned)(word & 0xffffffffull);
 #pragma unroll 1
-        for (int w = 0; w < d.world; ++w) {                                      // rank order: identical bits on every GPU
+        for (int w = 0; w < world(); ++w) {                                      // rank order: identical bits on every GPU
             const unsigned a0 = __shfl_sync(0xffffffffu, lo32, 4 * w), a1 = __shfl_sync(0xffffffffu, lo32, 4 * w + 1);
             acc += __longlong_as_double((long long)(((unsigned long long)a1 << 32) | a0));
         }
@@ -439,7 +446,7 @@ struct Ctx {
             const unsigned long long t0 = gtimer();
             int ok = aborted ? 0 : 1;
             double acc = 0.0, f0 = 0.0;
-            if (d.world == 1) barrier_single(ok, acc, f0, t0);
+            if (world() == 1) barrier_single(ok, acc, f0, t0);
             else              barrier_multi(ok, acc, f0, t0, remote_data);
             if (tid == 0) { pend_v = 0.0; pend_f = 0.0; }
             ok = __all_sync(0xffffffffu, ok);
@@ -480,7 +487,7 @@ struct Ctx {
     // (operand_sync(): a local one; or the cross-GPU reduction that was due anyway) publishes them to the local consumers.
     __device__ __forceinline__ void begin_push() { xtag += 1; }
     __device__ __forceinline__ void unpack_operand() {
-        if (d.world == 1 || d.push_plain) return;
+        if (world() == 1 || d.push_plain) return;
         const unsigned long long t0 = gtimer();
         const int nrem = d.n3 - d.nown;
         const long long total = (long long)d.r * nrem;
@@ -502,7 +509,7 @@ struct Ctx {
     }
     // publish a freshly built operand to every consumer: world == 1 -> the grid barrier; else unpack + local barrier
     __device__ __forceinline__ bool operand_sync() {
-        if (d.world == 1) return grid_sync();
+        if (world() == 1) return grid_sync();
         if (d.push_plain) return grid_sync(true);             // plain rows in the peers' Xt: the .sys-fenced barrier publishes them
         unpack_operand();
         return local_sync();
@@ -536,9 +543,9 @@ __device__ __forceinline__ void st_operand(const C& c, int i, bool act, const do
         const size_t rs = c.d.x_cam_major ? (size_t)c.d.r : 1;             // distance between the camera's three rows
         double* p = c.d.Xt + off;
         p[0] = x[0]; p[rs] = x[1]; p[2 * rs] = x[2];
-        if (c.d.world > 1) {
+        if (c.world() > 1) {
 #pragma unroll 1
-            for (int w = 0; w < c.d.world; ++w) {
+            for (int w = 0; w < c.world(); ++w) {
                 if (w == c.d.rank) continue;
                 if (c.d.push_plain) {
                     double* q = c.d.Xt_peer[w] + off;
@@ -557,7 +564,7 @@ __device__ __forceinline__ void st_out3(const C& c, int i, bool act, const doubl
     if (act) {
         const size_t off = (size_t)c.j * c.d.n3 + 3 * i;
 #pragma unroll 1
-        for (int w = 0; w < c.d.world; ++w) {
+        for (int w = 0; w < c.world(); ++w) {
             double* q = c.d.outR_peer[w] + off;
             q[0] = x[0]; q[1] = x[1]; q[2] = x[2];
         }
@@ -720,20 +727,40 @@ __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, b
 struct ObjArgs { const double* Ycur; const double* scur; double* Dout; };
 
 // MODE_HESS: from E_i = (Q X)_i finish ehess (trustregion.h:227-255) + ehess2rhess (:277-295); returns <P,Hp> share
-template <int RP, int NT>
-__device__ __forceinline__ double epi_hess(Ctx<RP, NT>& c, int i, const double (&E)[3], bool valid) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ double epi_hess(Ctx<RP, NT, MG>& c, int i, const double (&E)[3], bool valid) {
     const Dev& d = c.d;
     const int r = d.r, W = c.W;
     const bool act = c.act && valid;
     double y[3], p[3], dd[3];
     ld3(c.R(c.iY), i, r, c.j, act, y); ld3(c.R(V_P), i, r, c.j, act, p); ld3(c.R(c.iD), i, r, c.j, act, dd);
-    const double si = c.S(c.iS)[i], psi = c.S(S_PS)[i], gi = c.S(S_GS)[i];
+    const double si = c.S(c.iS)[i], gi = c.S(S_GS)[i];
+    double psi = c.S(S_PS)[i];
     double S[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) S[q] = c.s6[(size_t)i * 6 + q];
     double e[3], hr[3], t[3], sp[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { e[a] = 2.0 * E[a]; hr[a] = si * e[a] + psi * dd[a]; }
+    for (int a = 0; a < 3; ++a) e[a] = 2.0 * E[a];
+    if (d.e_rec) {
+        // two-barrier iteration: the product just computed is 2 Q X(r_new) (2 Q X(p_0) for the first product of a tCG solve).
+        // Finish the direction update here (trustregion.h:634-638: p = beta p - r) and keep E = 2 Q X(p) by its recurrence.
+        if (!c.erec_first) {
+            const double beta = c.erec_beta;
+            double rr[3], ep[3];
+            ld3(c.R(V_RR), i, r, c.j, act, rr); ld3(c.R(V_E), i, r, c.j, act, ep);
+            const double rsi = c.S(S_RS)[i];
+            __syncwarp();                                   // every lane of the sub-warp has read S_PS[i] before lane 0 rewrites it
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { p[a] = beta * p[a] - rr[a]; e[a] = beta * ep[a] - e[a]; }
+            psi = (i > 0) ? beta * psi - rsi : 0.0;
+            st3(c.R(V_P), i, r, c.j, act, p);
+            if (c.j == 0 && valid) c.S(S_PS)[i] = psi;
+        }
+        st3(c.R(V_E), i, r, c.j, act, e);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) hr[a] = si * e[a] + psi * dd[a];
     symv(S, p, sp);
 #pragma unroll
     for (int a = 0; a < 3; ++a) t[a] = hr[a] - sp[a];
@@ -756,8 +783,8 @@ __device__ __forceinline__ double epi_hess(Ctx<RP, NT>& c, int i, const double (
 }
 
 // MODE_OBJ: D_i = 2 E_i ; returns camera share of  <Q sR, sR> + lam (s^2-1)^2  (trustregion.h:162-170)
-template <int RP, int NT>
-__device__ __forceinline__ double epi_obj(Ctx<RP, NT>& c, int i, const double (&E)[3], const ObjArgs& oa, bool valid) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ double epi_obj(Ctx<RP, NT, MG>& c, int i, const double (&E)[3], const ObjArgs& oa, bool valid) {
     const Dev& d = c.d;
     const bool act = c.act && valid;
     double y[3];
@@ -774,8 +801,8 @@ __device__ __forceinline__ double epi_obj(Ctx<RP, NT>& c, int i, const double (&
 // Per-batch tail shared by both dense paths and the BSR path: `red` holds, per warp, the 3*RP sums of its (camera,
 // k-split) task; sub-warp slot q finishes batch camera q: adds the KS partial sums in fixed order and runs the
 // per-camera epilogue straight from shared memory — the Q.Y result never goes to HBM in MODE_HESS / MODE_OBJ.
-template <int RP, int NT, int MODE>
-__device__ __forceinline__ double qy_batch_epilogue(Ctx<RP, NT>& c, const ObjArgs& oa, int b0, int nvalid, int KS, int CB) {
+template <int RP, int NT, int MODE, bool MG>
+__device__ __forceinline__ double qy_batch_epilogue(Ctx<RP, NT, MG>& c, const ObjArgs& oa, int b0, int nvalid, int KS, int CB) {
     const Dev& d = c.d;
     double part = 0.0;
     if (c.warp * c.cpw < nvalid) {                        // warp-uniform
@@ -801,8 +828,8 @@ __device__ __forceinline__ double qy_batch_epilogue(Ctx<RP, NT>& c, const ObjArg
     return part;
 }
 
-template <int RP, int NT>
-__device__ __forceinline__ void warp_reduce_to_red(Ctx<RP, NT>& c, double (&acc)[3][RP]) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void warp_reduce_to_red(Ctx<RP, NT, MG>& c, double (&acc)[3][RP]) {
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -813,8 +840,8 @@ __device__ __forceinline__ void warp_reduce_to_red(Ctx<RP, NT>& c, double (&acc)
 }
 
 // ---- direct-load paths: dense without TMA (BSR = false) and block-CSR (BSR = true): all warps of the CTA stream
-template <int RP, int NT, int MODE, bool BSR>
-__device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs& oa) {
+template <int RP, int NT, int MODE, bool BSR, bool MG>
+__device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjArgs& oa) {
     const Dev& d = c.d;
     const int KS = d.KS, CB = d.CB;
     const int cslot = c.warp / KS, ks = c.warp % KS;
@@ -874,8 +901,8 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT>& c, const ObjArgs&
 // never drains between Q.Y phases: when a phase ends the producer immediately re-arms the first min(ST, uses) stages
 // with the NEXT phase's Q tiles (Q does not depend on the operand), so HBM keeps streaming while the CTA runs the
 // per-camera phases and waits in grid barriers; only the small operand boxes are issued after the barrier.
-template <int RP, int NT, int MODE>
-__device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa, const CUtensorMap* mapQ3, const CUtensorMap* mapX,
+template <int RP, int NT, int MODE, bool MG>
+__device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs& oa, const CUtensorMap* mapQ3, const CUtensorMap* mapX,
                                                bool prefetch_next) {
     const Dev& d = c.d;
     const int NWC = d.NWC, nprod = d.nprod;
@@ -1007,8 +1034,8 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT>& c, const ObjArgs& oa
 
 // PATH: 0 = dense through the TMA ring, 1 = dense by direct loads (qy_variant=1), 2 = block-CSR.  A kernel is compiled for one
 // path only, so the register budget of the persistent kernel is not set by the path it does not run.
-template <int RP, int NT, int MODE, int PATH>
-__device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa, const CUtensorMap* mapQ, const CUtensorMap* mapX,
+template <int RP, int NT, int MODE, int PATH, bool MG>
+__device__ __forceinline__ double qy_phase(Ctx<RP, NT, MG>& c, const ObjArgs& oa, const CUtensorMap* mapQ, const CUtensorMap* mapX,
                                            bool prefetch_next = true) {     // mapQ: array of 3 maps (box heights d.box_nb[])
     unsigned long long t0 = 0;
     if (blockIdx.x == 0 && c.tid == 0) t0 = gtimer();
@@ -1021,8 +1048,8 @@ __device__ __forceinline__ double qy_phase(Ctx<RP, NT>& c, const ObjArgs& oa, co
 }
 
 // shared-memory set-up (once per kernel): [per-CTA state vectors, if they fit][TMA ring + its mbarriers]
-template <int RP, int NT>
-__device__ __forceinline__ void ring_init(Ctx<RP, NT>& c, unsigned char* dyn_smem) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void ring_init(Ctx<RP, NT, MG>& c, unsigned char* dyn_smem) {
     const Dev& d = c.d;
     const int NWC = d.NWC;
     unsigned char* base = (unsigned char*)(((uintptr_t)dyn_smem + 127) & ~(uintptr_t)127);
@@ -1060,8 +1087,8 @@ __device__ __forceinline__ void ring_init(Ctx<RP, NT>& c, unsigned char* dyn_sme
     }
     __syncthreads();
 }
-template <int RP, int NT>
-__device__ __forceinline__ void ring_drain(Ctx<RP, NT>& c) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void ring_drain(Ctx<RP, NT, MG>& c) {
     const Dev& d = c.d;
     if (!d.use_tma) return;
     __syncthreads();

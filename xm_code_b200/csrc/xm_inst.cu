@@ -6,16 +6,18 @@
 
 using namespace xm;
 
-#if !defined(XM_INST_GROUP) || !defined(XM_INST_PATH)
-#error "compile with -DXM_INST_GROUP=0|1|2 -DXM_INST_PATH=0|1|2"
+#if !defined(XM_INST_GROUP) || !defined(XM_INST_PATH) || !defined(XM_INST_MG)
+#error "compile with -DXM_INST_GROUP=0|1|2 -DXM_INST_PATH=0|1|2 -DXM_INST_MG=0|1"
 #endif
 constexpr int kPath = XM_INST_PATH;
-#define XM_CAT_(g, p) xm_launch_group##g##_path##p
-#define XM_GROUP_FN(g, p) XM_CAT_(g, p)        // two levels: XM_INST_PATH is expanded before it is pasted
+constexpr bool kMG = (XM_INST_MG != 0);        // 0: the one-GPU instantiation (multi-GPU branches folded away); 1: what a communicator launches
+#define XM_CAT_(g, p, m) xm_launch_group##g##_path##p##_mg##m
+#define XM_GROUP_FN2(g, p, m) XM_CAT_(g, p, m)
+#define XM_GROUP_FN(g, p) XM_GROUP_FN2(g, p, XM_INST_MG)
 
 template <int RP, int NT>
 static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
-    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, NT, kPath> : (const void*)xm_ops_kernel<RP, NT, kPath>;
+    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, NT, kPath, kMG> : (const void*)xm_ops_kernel<RP, NT, kPath, kMG>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     if (kind == 0) {
@@ -29,7 +31,7 @@ static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opco
 // block-CSR kernels hold 3 accumulators per lane whatever the rank: 512 threads for every RP
 template <int RP>
 static cudaError_t launch_bsr(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
-    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, 512, kPath> : (const void*)xm_ops_kernel<RP, 512, kPath>;
+    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, 512, kPath, kMG> : (const void*)xm_ops_kernel<RP, 512, kPath, kMG>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     if (kind == 0) {

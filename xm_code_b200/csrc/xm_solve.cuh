@@ -16,8 +16,8 @@ struct QMaps { CUtensorMap m[3]; };   // Q tensor maps for the (at most three) d
             if (const int i = valid ? _b + (c).sw : _b; true)
 
 // ---- entry: wire layout (3N x r column-major) -> camera-block state
-template <int RP, int NT>
-__device__ __forceinline__ void phase_load_point(Ctx<RP, NT>& c, const double* R0, const double* s0) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void phase_load_point(Ctx<RP, NT, MG>& c, const double* R0, const double* s0) {
     const Dev& d = c.d;
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -31,8 +31,8 @@ __device__ __forceinline__ void phase_load_point(Ctx<RP, NT>& c, const double* R
     }
 }
 // ---- exit: camera-block state -> wire layout (every rank's output copy gets this CTA's cameras)
-template <int RP, int NT>
-__device__ __forceinline__ void phase_store_point(Ctx<RP, NT>& c, const double* Y, const double* s) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void phase_store_point(Ctx<RP, NT, MG>& c, const double* Y, const double* s) {
     const Dev& d = c.d;
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
@@ -43,14 +43,14 @@ __device__ __forceinline__ void phase_store_point(Ctx<RP, NT>& c, const double* 
         if (valid && c.j == 0) {
             const double si = s[i];
 #pragma unroll 1
-            for (int w = 0; w < d.world; ++w) d.outS_peer[w][i] = si;
+            for (int w = 0; w < c.world(); ++w) d.outS_peer[w][i] = si;
         }
     }
 }
 
 // ---- operand X = s_i * Y_i (for objective / gradient products): trustregion.h:152,375,677
-template <int RP, int NT>
-__device__ __forceinline__ void phase_operand_sR(Ctx<RP, NT>& c, const double* Y, const double* s) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void phase_operand_sR(Ctx<RP, NT, MG>& c, const double* Y, const double* s) {
     const Dev& d = c.d;
     c.begin_push();
     __syncthreads();
@@ -65,8 +65,8 @@ __device__ __forceinline__ void phase_operand_sR(Ctx<RP, NT>& c, const double* Y
 }
 
 // ---- line-search trial point: Ynew = MGS(Y - alpha * [0 .. 0 v]) ; operand = s * Ynew   (trustregion.h:360-383)
-template <int RP, int NT>
-__device__ __forceinline__ void phase_ls_trial(Ctx<RP, NT>& c, double alpha) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void phase_ls_trial(Ctx<RP, NT, MG>& c, double alpha) {
     const Dev& d = c.d;
     c.begin_push();
     __syncthreads();
@@ -89,8 +89,8 @@ __device__ __forceinline__ void phase_ls_trial(Ctx<RP, NT>& c, double alpha) {
 
 // ---- gradient phase at the current point, from D = 2 Q sR:
 //      grad (trustregion.h:186-194) + projection (:307-317) + CG initialisation (:476-485) + first operand (:229-234)
-template <int RP, int NT>
-__device__ __forceinline__ double phase_grad(Ctx<RP, NT>& c, bool build_operand) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ double phase_grad(Ctx<RP, NT, MG>& c, bool build_operand) {
     const Dev& d = c.d;
     const int r = d.r, W = c.W;
     double part = 0.0;
@@ -131,11 +131,12 @@ __device__ __forceinline__ double phase_grad(Ctx<RP, NT>& c, bool build_operand)
 }
 
 // ---- tCG update with step alpha (trustregion.h:605-610) and the new residual norm share (:625-626)
-template <int RP, int NT>
-__device__ __forceinline__ double phase_update(Ctx<RP, NT>& c, double alpha) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ double phase_update(Ctx<RP, NT, MG>& c, double alpha) {
     const Dev& d = c.d;
     const int r = d.r;
     double part = 0.0;
+    if (d.e_rec) c.begin_push();                // e_rec: this phase also builds the next product's operand X(r_new) = s r_R + r_s Y
     __syncthreads();
     XM_FOR_OWN_CAMERAS(c, i, valid) {
         const bool act = c.act && valid;
@@ -146,22 +147,32 @@ __device__ __forceinline__ double phase_update(Ctx<RP, NT>& c, double alpha) {
         for (int a = 0; a < 3; ++a) { v[a] += alpha * p[a]; rr[a] += alpha * hp[a]; hv[a] += alpha * hp[a]; }
         st3(c.R(V_V), i, r, c.j, act, v); st3(c.R(V_RR), i, r, c.j, act, rr); st3(c.R(V_HV), i, r, c.j, act, hv);
         if (act) part += rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2];
+        // every lane of the sub-warp computes the new scale residual (lane 0 stores it): the e_rec operand needs it in all lanes
+        double rsi = 0.0;
+        if (valid && i > 0) rsi = c.S(S_RS)[i] + alpha * c.S(S_HPS)[i];
+        __syncwarp();
         if (valid && c.j == 0 && i > 0) {
             const double psi = c.S(S_PS)[i], hpsi = c.S(S_HPS)[i];
             c.S(S_VS)[i] += alpha * psi;
-            const double rsi = c.S(S_RS)[i] + alpha * hpsi;
             c.S(S_RS)[i] = rsi;
             c.S(S_HVS)[i] += alpha * hpsi;
             const double t = rsi / c.S(c.iS)[i];
             part += t * t;
+        }
+        if (d.e_rec) {
+            double y[3];
+            ld3(c.R(c.iY), i, r, c.j, act, y);
+            const double si = valid ? c.S(c.iS)[i] : 0.0;
+            const double x[3] = {si * rr[0] + rsi * y[0], si * rr[1] + rsi * y[1], si * rr[2] + rsi * y[2]};
+            st_operand(c, i, act, x);
         }
     }
     return part;
 }
 
 // ---- boundary / negative-curvature exit: v += tau p ; hv += tau Hp  (trustregion.h:577-600)
-template <int RP, int NT>
-__device__ __forceinline__ void phase_tau(Ctx<RP, NT>& c, double tau) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void phase_tau(Ctx<RP, NT, MG>& c, double tau) {
     const Dev& d = c.d;
     const int r = d.r;
     __syncthreads();
@@ -177,8 +188,8 @@ __device__ __forceinline__ void phase_tau(Ctx<RP, NT>& c, double tau) {
 }
 
 // ---- new search direction p = beta p - r (trustregion.h:634-638) fused with the next operand s*P + ps*Y (:229-234)
-template <int RP, int NT>
-__device__ __forceinline__ void phase_dir(Ctx<RP, NT>& c, double beta) {
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ void phase_dir(Ctx<RP, NT, MG>& c, double beta) {
     const Dev& d = c.d;
     const int r = d.r;
     c.begin_push();
@@ -201,8 +212,8 @@ __device__ __forceinline__ void phase_dir(Ctx<RP, NT>& c, double beta) {
 
 // ---- model decrease share (trustregion.h:667-668) fused with the retraction (:341-351) and the next operand (:677)
 //      etaR = V, etas = vs, lr = 1  (general lr / eta pointers for the op-level hook)
-template <int RP, int NT>
-__device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const double* etaR, const double* etas, double lr,
+template <int RP, int NT, bool MG>
+__device__ __forceinline__ double phase_model_retract(Ctx<RP, NT, MG>& c, const double* etaR, const double* etas, double lr,
                                                       bool with_model) {
     const Dev& d = c.d;
     const int r = d.r;
@@ -241,17 +252,17 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT>& c, const doub
 // after a phase that built the Q.Y operand and is not followed by a reduction: publish the operand to its consumers
 #define XM_OSYNC(c) do { if (!(c).operand_sync()) goto xm_abort; } while (0)
 // reduction barrier right after a phase that also built the operand (plain-push protocol: it must publish the remote rows)
-#define XM_GSYNC_PUSHED(c) do { if (!(c).grid_sync((c).d.world > 1 && (c).d.push_plain != 0)) goto xm_abort; } while (0)
+#define XM_GSYNC_PUSHED(c) do { if (!(c).grid_sync((c).world() > 1 && (c).d.push_plain != 0)) goto xm_abort; } while (0)
 
 // ================================================================================================ the solver
-template <int RP, int NT, int PATH>
+template <int RP, int NT, int PATH, bool MG>
 __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
                                                          const __grid_constant__ CUtensorMap mapX) {
     __shared__ double red[(NT / 32) * 3 * RP];
     __shared__ double bsum[NT / 32];
     __shared__ double bcast[4];
     extern __shared__ unsigned char dyn_smem[];
-    Ctx<RP, NT> c(d, red, bsum, bcast);
+    Ctx<RP, NT, MG> c(d, red, bsum, bcast);
     ring_init(c, dyn_smem);
     const bool lead = (blockIdx.x == 0 && c.tid == 0);
     const unsigned long long t_kernel0 = gtimer();
@@ -324,11 +335,13 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
         endreason = 6; trstatus = 4;
         double vdotv = 0.0, vdotp = 0.0, pdotp = rdotr;
 
+        c.erec_first = true;
         for (i_inner = 0; i_inner < d.max_inner; ++i_inner) {                       // :559-664
             ObjArgs oa{nullptr, nullptr, nullptr};
             c.trace_on = (d.profile && lead && nqy >= 200 && nqy < 202);
             c.tr(1);
             const double ph = qy_phase<RP, NT, MODE_HESS, PATH>(c, oa, mapsQ.m, &mapX);
+            c.erec_first = false;
             c.tr(2);
             c.publish(ph); XM_GSYNC(c);
             c.tr(3);
@@ -346,15 +359,24 @@ __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__
             c.tr(4);
             const double pr = phase_update(c, alpha);
             c.tr(5);
-            c.publish(pr); XM_GSYNC(c);
+            if (d.e_rec) {                          // the operand X(r_new) rides on the <r,r> reduction barrier: two barriers per iteration
+                c.unpack_operand();
+                c.publish(pr); XM_GSYNC_PUSHED(c);
+            } else {
+                c.publish(pr); XM_GSYNC(c);
+            }
             c.tr(6);
             const double rdotr_new = c.collect();                                   // :626
             if (sqrt(rdotr_new) < gradnorm * fmin(gradnorm, 0.1)) { endreason = 3; break; }   // :627-630
             const double beta = rdotr_new / rdotr;
             c.tr(7);
-            phase_dir(c, beta);
-            c.tr(8);
-            XM_OSYNC(c);
+            if (d.e_rec) {
+                c.erec_beta = beta;                 // p = beta p - r and E = beta E - 2 Q X(r) happen in the next product's epilogue
+            } else {
+                phase_dir(c, beta);
+                c.tr(8);
+                XM_OSYNC(c);
+            }
             c.tr(9);
             const double nvv = vdotv + 2 * alpha * vdotp + alpha * alpha * pdotp;   // :642-644
             const double nvp = beta * (vdotp + alpha * pdotp);
@@ -409,7 +431,7 @@ xm_finish:
     phase_store_point(c, c.R(c.iY), c.S(c.iS));
     // multi-GPU: the result rows were pushed into every rank's output copy; nobody's host may read its copy (or launch the
     // next solve, which rewrites the peers' operand) before all of them have landed
-    if (d.world > 1) { if (!c.grid_sync(true)) goto xm_abort; }
+    if (c.world() > 1) { if (!c.grid_sync(true)) goto xm_abort; }
     c.save_epoch();
     if (lead) {
         DevStats& S = *d.stats;
@@ -432,8 +454,8 @@ xm_abort:
 //         2 = Riemannian gradient at (R0,s0)                        -> op_out_R = rgradR, op_out_s = rgrads, scalar[0] = gradnorm
 //         3 = Riemannian Hessian-vector at (R0,s0) along (P,ps)     -> op_out_R = HpR, op_out_s = Hps
 //         4 = retraction of (R0,s0) along (P,ps) with step op_lr    -> op_out_R = Rn, op_out_s = sn
-template <int RP, int NT, int PATH>
-__device__ __forceinline__ bool ops_body(Ctx<RP, NT>& c, const Dev& d, const QMaps& mapsQ, const CUtensorMap& mapX, const int opcode) {
+template <int RP, int NT, int PATH, bool MG>
+__device__ __forceinline__ bool ops_body(Ctx<RP, NT, MG>& c, const Dev& d, const QMaps& mapsQ, const CUtensorMap& mapX, const int opcode) {
     if (opcode == 0) {
         ObjArgs oa{nullptr, nullptr, nullptr};
         // op_repeat > 1 (xm_bench_qy): back-to-back products inside one launch, ring prefetch across them as in the solver
@@ -524,18 +546,18 @@ xm_abort:
     return false;
 }
 
-template <int RP, int NT, int PATH>
+template <int RP, int NT, int PATH, bool MG>
 __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
                                                        const __grid_constant__ CUtensorMap mapX, const int opcode) {
     __shared__ double red[(NT / 32) * 3 * RP];
     __shared__ double bsum[NT / 32];
     __shared__ double bcast[4];
     extern __shared__ unsigned char dyn_smem[];
-    Ctx<RP, NT> c(d, red, bsum, bcast);
+    Ctx<RP, NT, MG> c(d, red, bsum, bcast);
     ring_init(c, dyn_smem);
     bool ok = ops_body<RP, NT, PATH>(c, d, mapsQ, mapX, opcode);
     // multi-GPU: results were pushed to every rank and the peers' operand copies may still be in use — leave together
-    if (ok && d.world > 1) ok = c.grid_sync(true);
+    if (ok && c.world() > 1) ok = c.grid_sync(true);
     if (ok) c.save_epoch();
     else ring_drain(c);
 }
