@@ -5,7 +5,8 @@ Runs in two set-ups with the same assertions:
     with xm_comm_connect_ptrs, the collective calls issued from one thread per handle;
   * `torchrun --nproc-per-node W -m pytest tests/test_gpu_multi.py -m gpu`: one process per GPU, arenas exchanged as
     CUDA-IPC handles through torch.distributed (the bench.py set-up); every rank runs the same tests in lock-step.
-Skipped on a single-GPU box (the driver's -m gpu run): the single-GPU tests cover the same device code with world == 1.
+On a single-GPU box (the driver's -m gpu run) the same tests run on a LOOP-BACK team: two members on device 0 with 74 CTAs
+each (see Team), so the multi-GPU device code is exercised there as well.
 """
 import os
 from concurrent.futures import ThreadPoolExecutor
@@ -42,8 +43,23 @@ class Team:
             xdist.attach(h, n_cameras, max_r)
             self.handles = [h]
         else:
-            self.world = min(torch.cuda.device_count(), int(os.environ.get("XM_TEST_WORLD", "2")))
-            self.handles = [capi.Handle(device=k, **opts) for k in range(self.world)]
+            want = int(os.environ.get("XM_TEST_WORLD", "2"))
+            self.loopback = torch.cuda.device_count() < 2
+            if self.loopback:
+                # LOOP-BACK team on ONE GPU (the driver's single-GPU box): `want` members share device 0, each with at most
+                # 148 / want CTAs (one CTA per SM: both cooperative kernels are co-resident) and its own non-blocking stream.
+                # Same device code as a real multi-GPU run: barrier_multi, st_operand / unpack_operand, push_plain, the
+                # .sys-fenced final barrier; a scheduling failure would end in XM_ESYNC (watchdog), not in a hang.
+                self.world = want
+                sms = torch.cuda.get_device_properties(0).multi_processor_count
+                opts = dict(opts); opts["grid_ctas"] = min(opts.get("grid_ctas", 0) or sms // want, sms // want)
+                self.handles = [capi.Handle(device=0, **opts) for _ in range(self.world)]
+                self.streams = [torch.cuda.Stream(device=0) for _ in range(self.world)]
+                for h, st in zip(self.handles, self.streams):
+                    h.set_stream(st.cuda_stream)
+            else:
+                self.world = min(torch.cuda.device_count(), want)
+                self.handles = [capi.Handle(device=k, **opts) for k in range(self.world)]
             for k, h in enumerate(self.handles):
                 h.comm_init(k, self.world, n_cameras, max_r)
             ptrs = [h.comm_arena() for h in self.handles]
@@ -70,8 +86,8 @@ class Team:
 @pytest.fixture
 def team_factory():
     import torch
-    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (or torchrun)")
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
     made = []
 
     def make(n_cameras, max_r, **opts):

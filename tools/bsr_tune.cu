@@ -20,6 +20,7 @@
 
 struct P {
     int N, r, W, cpw;                 // cameras, rank, sub-warp width (power of two >= r), sub-warps per warp
+    int xs;                           // operand doubles per camera: 3r, or 3r rounded up to a multiple of 4 (32-byte sectors never straddled)
     const int* rowptr; const int* col; const double* val; const double* X; double* out;
 };
 
@@ -43,7 +44,7 @@ __global__ void k_ref(const P p) {
     for (int b = p.rowptr[i]; b < p.rowptr[i + 1]; ++b) {
         const int c = p.col[b];
         const double* q = p.val + (size_t)b * 16 + 4 * a;
-        acc += q[0] * p.X[(size_t)(3 * c) * p.r + j] + q[1] * p.X[(size_t)(3 * c + 1) * p.r + j] + q[2] * p.X[(size_t)(3 * c + 2) * p.r + j];
+        acc += q[0] * p.X[(size_t)c * p.xs + j] + q[1] * p.X[(size_t)c * p.xs + p.r + j] + q[2] * p.X[(size_t)c * p.xs + 2 * p.r + j];
     }
     p.out[(size_t)(3 * i + a) * p.r + j] = acc;
 }
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_direct(const P p) {      // 3
                     const int c = __ldg(p.col + b);
                     const double* blk = p.val + (size_t)b * 16;
                     ldg_v4(blk, q0[k]); ldg_v4(blk + 4, q1[k]); ldg_v4(blk + 8, q2[k]);
-                    if (act) { const double* xp = p.X + (size_t)(3 * c) * r + j; x[k][0] = xp[0]; x[k][1] = xp[r]; x[k][2] = xp[2 * r]; }
+                    if (act) { const double* xp = p.X + (size_t)c * p.xs + j; x[k][0] = xp[0]; x[k][1] = xp[r]; x[k][2] = xp[2 * r]; }
                 }
             }
 #pragma unroll
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(NT, 1) k_stage(const P p) {
                 const int bi = g0 + k * cpw + sw;
                 const int c = __shfl_sync(0xffffffffu, colreg, bi & 31);
                 x[k][0] = x[k][1] = x[k][2] = 0.0;
-                if (act && bi < nb) { const double* xp = p.X + (size_t)(3 * c) * r + j; x[k][0] = xp[0]; x[k][1] = xp[r]; x[k][2] = xp[2 * r]; }
+                if (act && bi < nb) { const double* xp = p.X + (size_t)c * p.xs + j; x[k][0] = xp[0]; x[k][1] = xp[r]; x[k][2] = xp[2 * r]; }
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -198,6 +199,7 @@ static float time_ms(F launch, int iters) {
 int main(int argc, char** argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 100000, deg = argc > 2 ? atoi(argv[2]) : 100, r = argc > 3 ? atoi(argv[3]) : 10;
     const int iters = argc > 4 ? atoi(argv[4]) : 20;
+    const int pad = argc > 5 ? atoi(argv[5]) : 0;          // 1: pad the operand's camera stride to a multiple of 32 bytes
     int W = 4; while (W < r) W <<= 1;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int SM = prop.multiProcessorCount;
@@ -214,24 +216,26 @@ int main(int argc, char** argv) {
         rowptr[i + 1] = (int)col.size();
     }
     const size_t nnzb = col.size();
-    std::vector<double> val(nnzb * 16, 0.0), X((size_t)3 * N * r);
+    const int xs = pad ? (3 * r + 3) / 4 * 4 : 3 * r;
+    std::vector<double> val(nnzb * 16, 0.0), X((size_t)xs * N);
     std::uniform_real_distribution<double> U(-1, 1);
     for (size_t b = 0; b < nnzb; ++b) for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) val[b * 16 + a * 4 + c] = U(rng);
     for (double& v : X) v = U(rng);
     int *d_rowptr, *d_col; double *d_val, *d_X, *d_out, *d_ref;
     CK(cudaMalloc(&d_rowptr, sizeof(int) * (N + 1))); CK(cudaMalloc(&d_col, sizeof(int) * nnzb)); CK(cudaMalloc(&d_val, sizeof(double) * nnzb * 16));
-    CK(cudaMalloc(&d_X, sizeof(double) * X.size())); CK(cudaMalloc(&d_out, sizeof(double) * X.size())); CK(cudaMalloc(&d_ref, sizeof(double) * X.size()));
+    const size_t nout = (size_t)3 * N * r;
+    CK(cudaMalloc(&d_X, sizeof(double) * X.size())); CK(cudaMalloc(&d_out, sizeof(double) * nout)); CK(cudaMalloc(&d_ref, sizeof(double) * nout));
     CK(cudaMemcpy(d_rowptr, rowptr.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_col, col.data(), sizeof(int) * nnzb, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_val, val.data(), sizeof(double) * nnzb * 16, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_X, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice));
-    P p{N, r, W, 32 / W, d_rowptr, d_col, d_val, d_X, d_ref};
+    P p{N, r, W, 32 / W, xs, d_rowptr, d_col, d_val, d_X, d_ref};
     const long long tot = (long long)N * 3 * r;
     k_ref<<<(unsigned)((tot + 255) / 256), 256>>>(p);
     CK(cudaDeviceSynchronize());
-    std::vector<double> ref(X.size()), got(X.size());
+    std::vector<double> ref(nout), got(nout);
     CK(cudaMemcpy(ref.data(), d_ref, sizeof(double) * ref.size(), cudaMemcpyDeviceToHost));
     p.out = d_out;
     const double bytes = (double)nnzb * 132 + 4.0 * (N + 1) + 2.0 * 8 * 3 * N * r;
-    printf("# N=%d nnzb=%zu r=%d W=%d  algorithmic bytes %.3f GB  SMs=%d\n", N, nnzb, r, W, bytes / 1e9, SM);
+    printf("# N=%d nnzb=%zu r=%d W=%d operand stride %d doubles per camera  algorithmic bytes %.3f GB  SMs=%d\n", N, nnzb, r, W, xs, bytes / 1e9, SM);
     auto report = [&](const char* name, float ms) {
         CK(cudaMemcpy(got.data(), d_out, sizeof(double) * got.size(), cudaMemcpyDeviceToHost));
         double err = 0, mx = 0;

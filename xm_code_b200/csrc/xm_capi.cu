@@ -15,19 +15,21 @@ using namespace xm;
 
 namespace xm {
 // ------------------------------------------------------------------------------------------------ layout kernels
-// Qp[i*ldq + k] = Qcm[i + ld*k]  (column-major user matrix -> padded row-major), 32x32 smem tiles, pad stays zero
-// (Qcm points at the first of `nrows` rows of the n3-column matrix: a rank's slab when the cameras are partitioned)
-__global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld, int nrows, int n3, double* __restrict__ Qp, int ldq) {
+// Qp[i*ldq + k0 + k] = Qcm[i + ld*k]  (column-major user matrix -> padded row-major), 32x32 smem tiles.  Qcm holds `ncols`
+// columns of `nrows` rows (a rank's row slab, and — on the host-upload path — one column panel starting at column k0 of the
+// full matrix); columns [ncols, nwrite) of the panel are written as zero padding.
+__global__ void xm_repack_q_kernel(const double* __restrict__ Qcm, long long ld, int nrows, int ncols, int k0, int nwrite,
+                                   double* __restrict__ Qp, int ldq) {
     __shared__ double tile[32][33];
     const int bi = blockIdx.y * 32, bk = blockIdx.x * 32;
     for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // read: consecutive threads along i (contiguous in col-major)
         const int k = bk + t, i = bi + threadIdx.x;
-        tile[t][threadIdx.x] = (i < nrows && k < n3) ? Qcm[(size_t)i + (size_t)ld * k] : 0.0;
+        tile[t][threadIdx.x] = (i < nrows && k < ncols) ? Qcm[(size_t)i + (size_t)ld * k] : 0.0;
     }
     __syncthreads();
     for (int t = threadIdx.y; t < 32; t += blockDim.y) {        // write: consecutive threads along k
         const int i = bi + t, k = bk + threadIdx.x;
-        if (i < nrows && k < ldq) Qp[(size_t)i * ldq + k] = (k < n3) ? tile[threadIdx.x][t] : 0.0;
+        if (i < nrows && k < nwrite) Qp[(size_t)i * ldq + k0 + k] = (k < ncols) ? tile[threadIdx.x][t] : 0.0;
     }
 }
 
@@ -189,6 +191,7 @@ extern "C" int xm_comm_connect_ptrs(xm_handle* h, void* const* arena_ptrs) {
         if (w == h->rank) continue;
         cudaPointerAttributes at;
         XM_CUDA(h, cudaPointerGetAttributes(&at, arena_ptrs[w]));
+        if (at.device == h->device) { h->peer_arena[w] = (char*)arena_ptrs[w]; continue; }   // loop-back member on the same GPU
         int can = 0;
         XM_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, at.device));
         if (!can) { h->err = "no peer access between the communicator's devices"; return XM_EUNSUPPORTED; }
@@ -267,18 +270,32 @@ static int set_q_common(xm_handle* h, int n3, int row0, int nrows, const double*
     const int ldq = (n3 + 63) / 64 * 64;
     int rc = ensure(h, &h->Qp, &h->Qp_cap, (size_t)nrows * ldq * sizeof(double));
     if (rc) return rc;
-    const double* src = q_slab;
-    if (!from_device) {
-        rc = ensure(h, &h->Qstage, &h->Qstage_cap, (size_t)nrows * n3 * sizeof(double));
+    if (from_device) {
+        dim3 blk(32, 8), grd((ldq + 31) / 32, (nrows + 31) / 32);
+        xm_repack_q_kernel<<<grd, blk, 0, h->stream>>>(q_slab, (long long)ld, nrows, n3, 0, ldq, h->Qp, ldq);
+        h->launches++;
+        XM_CUDA(h, cudaGetLastError());
+    } else {
+        // host matrix: column panels of at most ~128 MB go through ONE bounded staging buffer (H2D copy, then the re-layout
+        // kernel writes the panel's columns of the padded row-major copy) — no second full-size copy of Q in HBM
+        const size_t col_bytes = (size_t)nrows * sizeof(double);
+        int kc = (int)std::max<size_t>(32, ((size_t)128 << 20) / col_bytes / 32 * 32);
+        kc = std::min(kc, (n3 + 31) / 32 * 32);
+        rc = ensure(h, &h->Qstage, &h->Qstage_cap, (size_t)kc * col_bytes);
         if (rc) return rc;
-        XM_CUDA(h, cudaMemcpy2DAsync(h->Qstage, (size_t)nrows * sizeof(double), q_slab, (size_t)ld * sizeof(double),
-                                     (size_t)nrows * sizeof(double), n3, cudaMemcpyHostToDevice, h->stream));
-        src = h->Qstage; ld = nrows;
+        for (int k0 = 0; k0 < ldq; k0 += kc) {
+            const int ncopy = std::max(0, std::min(kc, n3 - k0));            // real columns in this panel (the rest is padding)
+            const int nwrite = std::min(kc, ldq - k0);
+            if (ncopy > 0)
+                XM_CUDA(h, cudaMemcpy2DAsync(h->Qstage, col_bytes, q_slab + (size_t)ld * k0, (size_t)ld * sizeof(double), col_bytes, ncopy,
+                                             cudaMemcpyHostToDevice, h->stream));
+            dim3 blk(32, 8), grd((nwrite + 31) / 32, (nrows + 31) / 32);
+            xm_repack_q_kernel<<<grd, blk, 0, h->stream>>>(h->Qstage, (long long)nrows, nrows, ncopy, k0, nwrite, h->Qp, ldq);
+            XM_CUDA(h, cudaGetLastError());
+            h->launches++;
+        }
+        XM_CUDA(h, cudaStreamSynchronize(h->stream));      // "copied": the caller may reuse its buffer when this returns
     }
-    dim3 blk(32, 8), grd((ldq + 31) / 32, (nrows + 31) / 32);
-    xm_repack_q_kernel<<<grd, blk, 0, h->stream>>>(src, (long long)ld, nrows, n3, h->Qp, ldq);
-    XM_CUDA(h, cudaGetLastError());
-    h->launches++;
     h->n3 = n3; h->N = n3 / 3; h->ldq = ldq; h->is_bsr = false;
     h->cam0 = c0; h->cam1 = c1;
     return XM_OK;
@@ -417,10 +434,16 @@ static int carve(xm_handle* h, int r, const Plan& p) {
                          align_up((size_t)kPartialBufs * (p.G + 1) * kPartialStride * sizeof(double), 256);
     bool fresh = false;
     if (h->ws_cap < total) {
+        // a member of a communicator sizes the workspace for the communicator's maximum rank at once: growing it later would
+        // cudaFree (a device-wide synchronisation) while a peer's persistent kernel may already be waiting for this rank
+        const size_t rcap = (h->world > 1) ? (size_t)std::max(r, h->comm_maxr) : (size_t)r;
+        const size_t want = std::max(total, kNumVecR * align_up(n3 * rcap * sizeof(double), 256) + align_up(N * 6 * sizeof(double), 256) + kNumVecS * vecS +
+                                                align_up(rcap * ldq * sizeof(double), 256) +
+                                                align_up((size_t)kPartialBufs * (p.G + 1) * kPartialStride * sizeof(double), 256));
         if (h->ws) cudaFree(h->ws);
         h->ws = nullptr; h->ws_cap = 0;
-        if (cudaMalloc(&h->ws, total) != cudaSuccess) { cudaGetLastError(); h->err = "workspace cudaMalloc failed"; return XM_ENOMEM; }
-        h->ws_cap = total; fresh = true;
+        if (cudaMalloc(&h->ws, want) != cudaSuccess) { cudaGetLastError(); h->err = "workspace cudaMalloc failed"; return XM_ENOMEM; }
+        h->ws_cap = want; fresh = true;
     }
     if (fresh || h->ws_r != r || h->ws_N != (int)N || h->ws_G != p.GT || h->ws_ldq != (int)ldq || h->ws_bsr != (int)h->is_bsr) {
         XM_CUDA(h, cudaMemsetAsync(h->ws, 0, total, h->stream));
@@ -485,7 +508,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
 }
 
 static int ensure_io(xm_handle* h, int r) {
-    const size_t bR = (size_t)h->n3 * r * sizeof(double), bS = (size_t)h->N * sizeof(double);
+    const int rcap = (h->world > 1) ? std::max(r, h->comm_maxr) : r;      // see carve(): never re-allocate inside a collective
+    const size_t bR = (size_t)h->n3 * rcap * sizeof(double), bS = (size_t)h->N * sizeof(double);
     if (h->io_cap_R < bR) {
         double** ps[] = {&h->io_R0, &h->io_Rout, &h->io_P};
         for (auto pp : ps) { if (*pp) cudaFree(*pp); *pp = nullptr; if (cudaMalloc(pp, bR) != cudaSuccess) { cudaGetLastError(); return XM_ENOMEM; } }

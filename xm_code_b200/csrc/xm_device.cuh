@@ -404,6 +404,11 @@ struct Ctx {
 #pragma unroll
                 for (int q = 0; q < MAXS; ++q) racc += w[q];                    // fixed slot order per lane
             }
+            // remote_data: the CTAs of this rank released plain stores into PEER memory (fence.sys + tagged slot).  The lanes that
+            // observed those slots acquire at system scope before the message below is sent, so the chain
+            // [CTA: stores, fence.sys, slot] -> [leader: slot, fence.sys, message] -> [consumer: message, fence.sys] orders the
+            // remote stores before every consumer's reads under the PTX memory model (not only empirically).
+            if (remote_data) asm volatile("fence.acq_rel.sys;" ::: "memory");
             racc = warpsum(racc);
             const double rf0 = __shfl_sync(0xffffffffu, my_flag, 0);            // only rank 0's flag is used (global CTA 0's clock)
             if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[1] += t - tseg; tseg = t; }
@@ -427,8 +432,10 @@ struct Ctx {
         }
         __syncwarp();
         if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[3] += t - tseg; tseg = t; }
-        // acquire what this GPU's CTAs wrote before they arrived (plain stores, consumed after the barrier through L1 / TMA)
-        if (lane == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        // acquire what this GPU's CTAs wrote before they arrived (plain stores, consumed after the barrier through L1 / TMA);
+        // remote_data: the lanes that read the messages acquire at system scope (the peers' plain stores into this GPU's memory)
+        if (remote_data) { if (lane < nw) asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+        else if (lane == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
         if (tid == 0 && d.profile) { const unsigned long long t = gtimer(); bseg[4] += t - tseg; }
         const unsigned lo32 = (unsigned)(word & 0xffffffffull);
 #pragma unroll 1

@@ -177,3 +177,147 @@ def bsr_to_dense(rowptr, colidx, vals) -> np.ndarray:
             j = colidx[b]
             Q[3 * i:3 * i + 3, 3 * j:3 * j + 3] = vals[b].T
     return Q
+
+
+# ------------------------------------------------------------------------------------------------ large problems (torch, on the GPU)
+# BAL-Final-sized inputs (13 682 cameras, dense Q = 13.5 GB) take minutes with the NumPy/SciPy route above.  The two
+# functions below restate the SAME generator and the SAME Schur assembly with torch tensor ops so they run on the
+# device in seconds.  They are plain torch (index_put_, cholesky, matmul): input preparation shared by both arms of
+# bench.py, not the product path (the product's own assembly is xm_create_matrix, xm_code_b200/csrc/xm_assemble.cu).
+# Everything is deterministic for a given (seed, device type): accumulations go through index_put_(accumulate=True),
+# which sorts on CUDA, and the selection of the observed landmarks uses an integer hash instead of a device RNG.
+
+def _hash_u32(torch, a, b, seed):
+    """Integer mixing of (a, b, seed) -> 32-bit keys (int64 tensors, broadcasting)."""
+    m = 0xFFFFFFFF
+    h = (a * 0x9E3779B1 + b * 0x85EBCA77 + (seed + 1) * 0xC2B2AE3D) & m
+    h = h ^ (h >> 15)
+    h = (h * 0x2C1B3C6D) & m
+    h = h ^ (h >> 12)
+    h = (h * 0x297A2D39) & m
+    h = h ^ (h >> 15)
+    return h
+
+
+def synthetic_sfm_torch(n_cameras: int, n_landmarks: int | None = None, obs_per_camera: int = 60, turns: float = 2.0,
+                        noise: float = 2e-3, seed: int = 0, device=None, chunk: int = 256):
+    """The object-centric capture of ``synthetic_sfm`` (same geometry, same observation model) with the visibility test
+    and the choice of the observed landmarks done by batched tensor ops on `device`.  Returns numpy arrays like
+    ``synthetic_sfm`` (the observation lists are O(60 N): small)."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    rng = np.random.default_rng(seed)
+    N = int(n_cameras)
+    M = int(n_landmarks) if n_landmarks else max(8 * N, 64)
+    u = rng.standard_normal((M, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    p = u * (1.0 + 0.1 * rng.standard_normal((M, 1)))
+    phi = np.linspace(0.0, 2.0 * np.pi * turns, N, endpoint=False) + 0.02 * rng.standard_normal(N)
+    elev = 0.6 * np.sin(np.linspace(0.0, 2.0 * np.pi, N)) + 0.05 * rng.standard_normal(N)
+    rad = 2.2 + 0.1 * rng.standard_normal(N)
+    cpos = np.stack([rad * np.cos(elev) * np.cos(phi), rad * np.cos(elev) * np.sin(phi), rad * np.sin(elev)], axis=1)
+    z = -cpos / np.linalg.norm(cpos, axis=1, keepdims=True)
+    up = np.array([0.0, 0.0, 1.0])[None, :] + 0.15 * rng.standard_normal((N, 3))
+    x = np.cross(up, z); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    R = np.stack([x, y, z], axis=2)
+    s = np.concatenate([[1.0], rng.uniform(0.8, 1.25, N - 1)])
+    t = cpos.copy()
+    # visibility (near-side cap) + hashed choice of obs_per_camera landmarks per camera, `chunk` cameras at a time
+    ut = torch.from_numpy(u).to(dev)
+    cn = torch.from_numpy(-z).to(dev)                    # unit vector from the origin to the camera
+    lm_ids = torch.arange(M, device=dev, dtype=torch.int64)[None, :]
+    k = min(obs_per_camera, M)
+    BIG = float(1 << 40)
+    cam_l, lm_l = [], []
+    for c0 in range(0, N, chunk):
+        c1 = min(N, c0 + chunk)
+        vis = (cn[c0:c1] @ ut.T) > 0.55
+        ci = torch.arange(c0, c1, device=dev, dtype=torch.int64)[:, None]
+        key = _hash_u32(torch, ci, lm_ids, seed).to(torch.float64)
+        key = torch.where(vis, key, torch.full_like(key, BIG))
+        val, idx = torch.topk(key, k, dim=1, largest=False)
+        ok = val < BIG
+        cam_l.append(ci.expand(-1, k)[ok]); lm_l.append(idx[ok])
+    cam = torch.cat(cam_l); lm = torch.cat(lm_l)
+    cnt = torch.bincount(lm, minlength=M)
+    keep = cnt[lm] >= 2
+    cam, lm = cam[keep].cpu().numpy(), lm[keep].cpu().numpy()
+    order = np.lexsort((lm, cam))
+    cam, lm = cam[order], lm[order]
+    used = np.unique(lm)
+    remap = -np.ones(M, dtype=np.int64); remap[used] = np.arange(used.size)
+    lm = remap[lm]; p = p[used]; M = used.size
+    p = p - t[0]; t = t - t[0]
+    pt = np.einsum("nba,nb->na", R[cam], p[lm] - t[cam]) / s[cam, None] + noise * rng.standard_normal((cam.size, 3))
+    w = np.ones(cam.size)
+    return dict(N=N, M=M, cam=cam, lm=lm, w=w, pt=pt, R=R, s=s, t=t, p=p)
+
+
+def q_from_observations_torch(n_cameras: int, n_landmarks: int, cam, lm, w, pt, device=None):
+    """``q_from_observations`` on `device` with torch: returns the dense 3N x 3N float64 Q as a torch tensor (symmetric, so
+    its memory is both the row-major and the column-major matrix).  Peak memory ~ 2.7 x the matrix."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    N, M = int(n_cameras), int(n_landmarks)
+    f64 = torch.float64
+    cam_t = torch.as_tensor(np.asarray(cam, dtype=np.int64), device=dev)
+    lm_t = torch.as_tensor(np.asarray(lm, dtype=np.int64), device=dev)
+    w_t = torch.as_tensor(np.asarray(w, dtype=np.float64), device=dev)
+    pt_t = torch.as_tensor(np.asarray(pt, dtype=np.float64), device=dev)
+    nobs = cam_t.numel()
+    n3 = 3 * N
+    wp = w_t[:, None] * pt_t                                              # (nobs, 3)
+    dl = torch.zeros(M, dtype=f64, device=dev).index_put_((lm_t,), w_t, accumulate=True)
+    dc = torch.zeros(N, dtype=f64, device=dev).index_put_((cam_t,), w_t, accumulate=True)
+    if bool((dl <= 0).any()):
+        raise ValueError("every landmark needs at least one observation")
+    # ordered pairs (a, b) of observations of the same landmark
+    order = torch.argsort(lm_t, stable=True)
+    lm_s = lm_t[order]
+    deg = torch.bincount(lm_s, minlength=M)
+    start = torch.cumsum(deg, 0) - deg                                    # first sorted position of each landmark
+    d_a = deg[lm_s]                                                       # group size of each sorted observation
+    a_pos = torch.repeat_interleave(torch.arange(nobs, device=dev), d_a)
+    off = torch.cumsum(d_a, 0) - d_a
+    b_pos = start[lm_s][a_pos] + (torch.arange(a_pos.numel(), device=dev) - off[a_pos])
+    a = order[a_pos]; b = order[b_pos]
+    inv_dl = 1.0 / dl[lm_t[a]]
+    ca, cb = cam_t[a], cam_t[b]
+    three = torch.arange(3, device=dev)
+    Q = torch.zeros((n3, n3), dtype=f64, device=dev)
+    # T1 = Vl Dl^-1 Vl^T : block (ca, cb) += wp_a wp_b^T / dl ;  Q starts as -T1
+    blk = -(wp[a][:, :, None] * wp[b][:, None, :]) * inv_dl[:, None, None]
+    rows = (3 * ca)[:, None, None] + three[None, :, None]
+    cols = (3 * cb)[:, None, None] + three[None, None, :]
+    Q.view(-1).index_put_(((rows * n3 + cols).reshape(-1),), blk.reshape(-1), accumulate=True)
+    del blk, rows, cols
+    # Q1 on the diagonal blocks
+    q1 = w_t[:, None, None] * pt_t[:, :, None] * pt_t[:, None, :]
+    rows = (3 * cam_t)[:, None, None] + three[None, :, None]
+    cols = (3 * cam_t)[:, None, None] + three[None, None, :]
+    Q.view(-1).index_put_(((rows * n3 + cols).reshape(-1),), q1.reshape(-1), accumulate=True)
+    del q1, rows, cols
+    # reduced camera Laplacian Sc = diag(dc) - W Dl^-1 W^T and B = Vc + Vl Dl^-1 W^T
+    Sc = torch.zeros((N, N), dtype=f64, device=dev)
+    Sc.view(-1).index_put_((ca * N + cb,), -(w_t[a] * w_t[b] * inv_dl), accumulate=True)
+    Sc.diagonal().add_(dc)
+    B = torch.zeros((n3, N), dtype=f64, device=dev)
+    vals = -(wp[a] * (w_t[b] * inv_dl)[:, None])                          # (pairs, 3)
+    rows = (3 * ca)[:, None] + three[None, :]
+    B.view(-1).index_put_(((rows * N + cb[:, None]).reshape(-1),), vals.reshape(-1), accumulate=True)
+    rows = (3 * cam_t)[:, None] + three[None, :]
+    B.view(-1).index_put_(((rows * N + cam_t[:, None]).reshape(-1),), wp.reshape(-1), accumulate=True)
+    del vals, rows, a, b, ca, cb, a_pos, b_pos
+    Bb = B[:, 1:].contiguous(); del B
+    L = torch.linalg.cholesky(Sc[1:, 1:]); del Sc
+    Z = torch.cholesky_solve(Bb.T.contiguous(), L); del L                  # (N-1) x 3N
+    Q.addmm_(Bb, Z, alpha=-1.0); del Bb, Z
+    Q = (Q + Q.T).mul_(0.5)
+    return Q
+
+
+def synthetic_dense_q_torch(n_cameras: int, seed: int = 0, obs_per_camera: int = 60, n_landmarks=None, noise: float = 2e-3, device=None):
+    """Device-side twin of ``synthetic_dense_q`` (hashed landmark choice: a different, equally shaped problem)."""
+    prob = synthetic_sfm_torch(n_cameras, n_landmarks=n_landmarks, obs_per_camera=obs_per_camera, noise=noise, seed=seed, device=device)
+    Q = q_from_observations_torch(prob["N"], prob["M"], prob["cam"], prob["lm"], prob["w"], prob["pt"], device=device)
+    return Q, prob
