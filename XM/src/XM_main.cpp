@@ -9,6 +9,7 @@
 #include <pybind11/pybind11.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
@@ -76,48 +77,21 @@ int run(const std::string& dataset_path, unsigned max_rank, double tol, double l
     H.check(xm_set_q_dense(H.h, n3, Q.data(), n3), "xm_set_q_dense");
     std::vector<double>().swap(Q);
 
-    unsigned o = 3;
-    std::vector<double> R0((size_t)n3 * o, 0.0), s0(n, 1.0), v(n3, 0.0);
-    if (mode == Mode::Rebuttle) {     // XM_main.cu:61-63: loaded, then overwritten by the identity at o == 3 (:95-103)
+    std::vector<double> s_ini;
+    if (mode == Mode::Rebuttle) {     // XM_main.cu:61-63: loaded, then R0 is overwritten by the identity at o == 3 (:95-103)
         std::vector<double> t; int rr, cc;
         load_bin(dataset_path + "/R_ini.bin", t, rr, cc);
-        if (load_bin(dataset_path + "/s_ini.bin", t, rr, cc) && (int)t.size() == n) s0 = t;
+        if (load_bin(dataset_path + "/s_ini.bin", t, rr, cc) && (int)t.size() == n) s_ini = t;
     }
-    double gradtol = tol, primal = 0.0;
-    int status = 0;
-    while (o <= max_rank || mode == Mode::Rank3) {
-        std::cout << "+++++++++++++++++++++++++++++++++" << std::endl;
-        std::cout << "Solve TR with Rank   " << o << std::endl;
-        std::cout << "+++++++++++++++++++++++++++++++++" << std::endl;
-        std::vector<double> R((size_t)n3 * o), s(n);
-        double ls_step = 1.0;
-        if (o == 3) {
-            std::fill(R0.begin(), R0.end(), 0.0);
-            for (int i = 0; i < n; ++i) { R0[3 * i] = 1.0; R0[3 * i + n3 + 1] = 1.0; R0[3 * i + 2 * (size_t)n3 + 2] = 1.0; }
-            ls_step = 0.0;
-        }
-        xm_stats st;
-        H.check(xm_trust_region(H.h, (int)o, R0.data(), s0.data(), lam, &gradtol, ls_step, v.data(), max_time,
-                                R.data(), s.data(), &primal, &st, nullptr), "xm_trust_region");
-        if (mode == Mode::Rank3) { R0 = R; s0 = s; o += 1; break; }
-        if (primal < 0) { status = -2; o += 1; break; }                       // line search failed (:244-247)
-        banner("Check Eigen value");
-        int certified = 0; double mineig = 0, dual = 0, gap = 0;
-        H.check(xm_certify(H.h, (int)o, R.data(), s.data(), lam, primal, v.data(), &mineig, &dual, &gap, &certified), "xm_certify");
-        if (certified) {
-            o += 1; R0 = R; s0 = s; status = 1;
-            break;
-        } else if (o < max_rank) {
-            R0.assign((size_t)n3 * (o + 1), 0.0);                             // zero-padded new column (:265-269)
-            std::copy(R.begin(), R.end(), R0.begin());
-            s0 = s;
-            xm_escape_scale(n, v.data(), s.data());                           // DecentDirectionKernal (:271)
-        } else {
-            R0 = R; s0 = s; status = 2;
-        }
-        o += 1;
-    }
-    if (o > max_rank && mode != Mode::Rank3) std::cout << "BM stoped because max rank" << std::endl;
+    // the staircase itself lives behind the C-ABI (xm_solve): the same code serves block-CSR operators and communicators
+    const int cap = (int)std::max(3u, std::min(max_rank, 20u));
+    std::vector<double> R0((size_t)n3 * cap), s0(n);
+    xm_solve_result res;
+    const int cmode = mode == Mode::Full ? XM_MODE_FULL : mode == Mode::Rank3 ? XM_MODE_RANK3 : XM_MODE_REBUTTLE;
+    H.check(xm_solve(H.h, cmode, (int)max_rank, tol, lam, max_time, s_ini.empty() ? nullptr : s_ini.data(), XM_CERT_AUTO,
+                     R0.data(), s0.data(), &res), "xm_solve");
+    const int status = res.status;
+    const unsigned o = (unsigned)res.rank + 1;
     save_bin(out + "R.bin", R0.data(), n3, (int)(o - 1));
     std::cout << "saved R" << std::endl;
     save_bin(out + "s.bin", s0.data(), n, 1);

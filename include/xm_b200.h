@@ -9,8 +9,10 @@
  *   xm_qy               <- DnMatDnMat (cublasDgemm, M=K=3N, N=r)                                XM/include/Dense/matmul.h:42-87
  *   xm_trust_region     <- XMtrustregion(C,R0,s0,R,s,lam,gradtol&,ls_step,v,&primal,maxtime)    XM/include/XM/trustregion.h:77-724
  *   xm_op_*             <- the lambdas objc/grad/projection/ehess+ehess2rhess/retraction        XM/include/XM/trustregion.h:162-351
- *   xm_certify          <- checkeig(C,sR,lam,v,primal)                                          XM/include/XM/checkeig.h:42-368
+ *   xm_certify(_ex)     <- checkeig(C,sR,lam,v,primal)                                          XM/include/XM/checkeig.h:42-368
+ *   xm_solve            <- solve / solve_rank3 / solve_rebuttle (the rank staircase)           XM/src/XM_main.cu:35-401
  *   xm_escape_scale     <- DecentDirectionKernal                                                XM/src/XM_main.cu:8-16
+ *   xm_create_matrix    <- create_matrix(weight, edges, landmarks, output_path)                 utils/creatematrix.py:52-341
  *   xm_recover          <- recover_XM(Q,R,s,Abar,lam)                                           utils/recoversolution.py:4-86
  *   xm_residuals        <- the per-observation error of the XM^2 outlier cut                    3_test_colmap_glomap.py:304-316
  *
@@ -66,6 +68,10 @@ typedef struct xm_options {
     int qy_variant;         /* dense Q.Y path: 0 = auto (2-D TMA ring + cross-phase prefetch), 1 = direct streaming loads */
     int vec_in_global;      /* 1 = keep the per-camera state vectors in HBM/L2 even when they would fit in shared memory */
     int profile;            /* 1 = fine-grained in-kernel phase timers (xm_stats.phase_ms); costs a few percent */
+    int three_barrier_tcg;  /* 0 (default) = two grid barriers per tCG iteration: E = 2 Q X(p) is kept by the recurrence
+                               E <- beta E - 2 Q X(r_new), so the product's operand is built from the new residual and rides on the
+                               <r,r> reduction barrier (same iterates up to rounding; measured +5 % on the latency-bound config);
+                               1 = the reference's order of operations: operand from the new direction, three barriers */
 } xm_options;
 
 typedef struct xm_log_rec { /* one line of the reference's stdout table (trustregion.h:487-526) */
@@ -111,7 +117,7 @@ int  xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, const int* 
  * torch.distributed all_gather) -> xm_comm_connect -> xm_set_q_* -> xm_trust_region* / xm_qy* / xm_op_*.  Every compute
  * call is COLLECTIVE: all ranks make the same call with the same (full-size) vector arguments; every rank receives the
  * full result.  xm_set_q_dense / xm_set_q_bsr given the whole matrix upload only the rank's rows; xm_set_q_dense_slab
- * takes the rank's row slab alone.  xm_certify is single-GPU only (XM_EUNSUPPORTED on a communicator). */
+ * takes the rank's row slab alone.  xm_certify on a communicator uses the iterative eigen-solver (collective). */
 #define XM_IPC_HANDLE_BYTES 64
 #define XM_MAX_WORLD 8
 /* cameras [cam_lo, cam_hi) of `rank` when each of `world` ranks runs ctas_per_rank CTAs (pure host function, no GPU) */
@@ -163,6 +169,49 @@ int  xm_op_retract(xm_handle* h, int r, const double* R, const double* s, const 
  * eigenvalue of the dual slack.  certified_out: 1/0. */
 int  xm_certify(xm_handle* h, int r, const double* R, const double* s, double lam, double primal,
                 double* v_out, double* min_eig_out, double* dual_out, double* gap_out, int* certified_out);
+/* Certificate with a chosen eigen-solver and a report.  XM_CERT_DENSE: cusolverDnDsyevd on the assembled 3N x 3N dual slack
+ * like checkeig.h:303-318 (one GPU, dense Q, O(N^3)).  XM_CERT_ITERATIVE: block Davidson on the operator S X = Q X + blockdiag X
+ * (<= 20 columns per product, block-Jacobi preconditioner, vectors resident in HBM): dense or block-CSR Q, one GPU or a
+ * communicator (collective: every rank makes the same call and takes the same decision).  XM_CERT_AUTO (what xm_certify uses):
+ * dense for a dense one-GPU Q with 3N <= 6000, iterative otherwise. */
+enum { XM_CERT_AUTO = 0, XM_CERT_DENSE = 1, XM_CERT_ITERATIVE = 2 };
+typedef struct xm_cert_info {
+    int certified;          /* checkeig.h:349-368 */
+    int method;             /* XM_CERT_DENSE or XM_CERT_ITERATIVE: what actually ran */
+    int products;           /* Q.Y products used (each <= 20 columns) */
+    int converged;          /* iterative: the r + 1 lowest Ritz pairs reached the residual tolerance */
+    double min_eig, dual, gap;
+    double residual;        /* iterative: largest residual norm among the r + 1 lowest Ritz pairs at exit */
+    double ms;              /* device time of the whole call (CUDA events on the handle's stream) */
+} xm_cert_info;
+int  xm_certify_ex(xm_handle* h, int r, const double* R, const double* s, double lam, double primal, int method,
+                   double* v_out, xm_cert_info* info_out);
+/* 3 x 3 diagonal blocks of the operator: out[9 i + 3 a + b] = Q[3i + a, 3i + b] (host buffer, 9 N doubles). */
+int  xm_op_diag_blocks(xm_handle* h, double* out9N);
+
+/* The rank staircase of the reference's entry points in one call (XM_main.cu:180-310 solve, :312-401 solve_rank3,
+ * :35-178 solve_rebuttle): rank 3 from the identity, certificate, zero-padded escalation along the escape direction, ... on
+ * whatever operator the handle holds (dense / block-CSR, one GPU / a communicator — then collective).  s_init: N doubles or
+ * NULL (solve_rebuttle's s_ini.bin).  R_out: capacity 3N x max(max_rank, 3) doubles, the first 3N x res->rank are the result
+ * (column-major); s_out: N.  res->status: 1 certified, 2 max rank reached uncertified, 0 n/a (rank-3 mode), -2 line search failed. */
+enum { XM_MODE_FULL = 0, XM_MODE_RANK3 = 1, XM_MODE_REBUTTLE = 2 };
+typedef struct xm_solve_result {
+    int rank, status, n_solves, certified, cert_method;
+    int tcg_iters_total, qy_products_total, cert_products_total;
+    double primal, gradnorm, min_eig, dual, gap;
+    double solve_ms_total, cert_ms_total;
+} xm_solve_result;
+int  xm_solve(xm_handle* h, int mode, int max_rank, double tol, double lam, double max_time, const double* s_init,
+              int cert_method, double* R_out, double* s_out, xm_solve_result* res);
+
+/* Q assembly (create_matrix, utils/creatematrix.py:52-341) on the device: observations of the bipartite (camera, landmark)
+ * graph -> the 3N x 3N SDP data matrix Q = Q1 - Vbar Lbar^-1 Vbar^T.  cam, lm: 0-based (n_obs); w: n_obs; pts: n_obs x 3 ROW-major
+ * camera-frame points (host arrays).  The assembled matrix BECOMES THE HANDLE'S OPERATOR (as after xm_set_q_dense): a solve can
+ * follow without a host round trip.  Q_out (host, 3N x 3N column-major) and Abar_out (host, (N + M - 1) x 3N column-major: the
+ * reference's Abar.bin, dense — small problems only) may be NULL; assemble_ms_out (may be NULL): device time of the assembly. */
+int  xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, int64_t n_obs, const int* cam, const int* lm,
+                      const double* w, const double* pts, double* Q_out, double* Abar_out, double* assemble_ms_out);
+
 /* Solution recovery (recover_XM): rank-r -> 3 (top-3 eigenvectors of (sR)^T(sR)), per-camera scale ||block||_F / sqrt(3),
  * anchoring by camera 0, projection of every 3x3 block to O(3) (polar factor U V^T), global sign by majority of det, and
  * [t p] = Abar (sR)^T.  R: 3N x r col-major; s: N.  Abar: abar_rows x 3N COLUMN-MAJOR (abar_rows = N + M - 1, the

@@ -28,8 +28,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(capi.XmOptions) == 10 * 4
+    assert ctypes.sizeof(capi.XmOptions) == 11 * 4
     assert ctypes.sizeof(capi.XmLogRec) == 4 * 4 + 3 * 8
+    assert ctypes.sizeof(capi.XmCertInfo) == 4 * 4 + 5 * 8 and ctypes.sizeof(capi.XmSolveResult) == 8 * 4 + 7 * 8
     assert ctypes.sizeof(capi.XmStats) == 5 * 4 + 4 + 5 * 8 + 4 * 4 + 4 * 8   # 5 ints + pad, 5 doubles, 4 ints, 4 doubles
 
 

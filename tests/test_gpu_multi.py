@@ -245,25 +245,29 @@ def test_rank_escalation_line_search_path(team_factory):
         check_point(got, ref, primal_rel=1e-8, s_abs=1e-6, x_abs=1e-5)
 
 
-def test_certify_is_refused_on_a_communicator(team_factory):
-    from xm_code_b200 import capi
-    rng = np.random.default_rng(1)
-    N = 50
-    Q = rand_psd(150, rng)
-    Y, s = rand_point(N, 3, rng)
-    t = team_factory(N, 3)
+def test_iterative_certificate_on_a_communicator(team_factory):
+    """xm_certify on a communicator = the iterative eigen-solver, collective: every rank gets the oracle's decision and numbers."""
+    rng = np.random.default_rng(11)
+    N = 60
+    A = rng.standard_normal((3 * N, 3 * N + 2))
+    Q = A @ A.T / (3 * N)
+    res3 = xo.trust_region(Q, xo.identity_init(N, 3), np.ones(N), 0.0, 1e-7)
+    R = xo.from_blocks(res3.Y)
+    ref = xo.certificate(Q, R * np.repeat(res3.s, 3)[:, None], 0.0, res3.primal)
+    t = team_factory(N, 8)
     t.call("set_q_dense", Q)
-    with pytest.raises(capi.XmError):
-        t.handles[0].certify(xo.from_blocks(Y), s, 0.0, 1.0)
+    out = t.call("certify", R, res3.s, 0.0, res3.primal)
+    for c in out:
+        assert c["method"] == "iterative" and c["converged"] and c["certified"] == ref["certified"]
+        assert abs(c["min_eig"] - ref["min_eig"]) < 1e-8 and abs(c["dual"] - ref["dual"]) < 1e-9
+        assert min(np.abs(c["v"] - ref["v"]).max(), np.abs(c["v"] + ref["v"]).max()) < 1e-5
+    if len(out) > 1:
+        assert out[0]["min_eig"] == out[1]["min_eig"] and out[0]["products"] == out[1]["products"]      # identical iteration on every rank
 
 
-def test_python_staircase_on_a_communicator(team_factory):
-    """solver.solve_arrays with the matrix-free certificate on a communicator (one process per GPU only: SciPy serialises
-    ARPACK calls inside a process with a lock held across the operator callbacks, so two ranks in ONE process would wait
-    for each other's collective forever)."""
-    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        pytest.skip("torchrun only")
-    from xm_code_b200 import solver
+def test_staircase_on_a_communicator(team_factory):
+    """xm_solve (the rank staircase incl. the certificate) with the cameras partitioned: same ranks, statuses and optimum as the
+    oracle's staircase, on every rank."""
     rng = np.random.default_rng(11)
     N = 30
     A = rng.standard_normal((3 * N, 3 * N + 2))
@@ -271,7 +275,7 @@ def test_python_staircase_on_a_communicator(team_factory):
     ref = xo.solve(Q, 5, 1e-7, 0.0)
     t = team_factory(N, 5)
     t.call("set_q_dense", Q)
-    out = solver.solve_arrays(t.handles[0], 5, 1e-7, 0.0)
-    assert out["certificate_method"] == "lanczos"
-    assert out["rank"] == ref["rank"] and out["status"] == ref["status"]
-    assert abs(out["trace"][-1].primal - ref["trace"][-1].primal) <= 1e-5 * abs(ref["trace"][-1].primal)
+    for out in t.call("solve", 5, 1e-7, 0.0):
+        assert out["certificate_method"] == "iterative"
+        assert out["rank"] == ref["rank"] and out["status"] == ref["status"]
+        assert abs(out["primal"] - ref["trace"][-1].primal) <= 1e-5 * abs(ref["trace"][-1].primal)

@@ -146,6 +146,14 @@ def test_refine_host_logic_with_oracle_standins(tmp_path, monkeypatch):
         o = xo.recover(R, np.asarray(s).reshape(-1), Abar)
         return o["R"], o["s"], o["p"], o["t"]
 
+    def host_create_matrix(weight, edges, landmarks, output_path, handle=None):      # the product assembles on the GPU (xm_create_matrix)
+        e = np.asarray(edges)
+        Q, Abar = problems.q_from_observations(int(e[:, 0].max()), int(e[:, 1].max()), e[:, 0] - 1, e[:, 1] - 1, weight, landmarks, return_abar=True)
+        binio.save_matrix_to_bin(output_path + "/Abar.bin", Abar); binio.save_matrix_to_bin(output_path + "/Q.bin", Q)
+        return Q, Abar
+
+    from xm_code_b200 import creatematrix as cmmod
+    monkeypatch.setattr(cmmod, "create_matrix", host_create_matrix)
     monkeypatch.setattr(recmod, "recover_XM", oracle_recover)
     monkeypatch.setattr(xm2, "observation_errors", lambda e, l, w, R, s, t, p, handle=None: xo.observation_errors(e, l, w, R, s, t, p))
     prob = problems.synthetic_sfm(30, n_landmarks=260, obs_per_camera=60, seed=9)

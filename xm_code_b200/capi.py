@@ -22,7 +22,7 @@ EXIT_CODES = {1: "gradtol", 2: "rdotr_tiny", 3: "maxtime", 4: "model_increase", 
 class XmOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("grid_ctas", C.c_int), ("ksplit", C.c_int), ("replicate_stale_sr", C.c_int),
                 ("verbose", C.c_int), ("max_outer", C.c_int), ("max_inner", C.c_int), ("qy_variant", C.c_int),
-                ("vec_in_global", C.c_int), ("profile", C.c_int)]
+                ("vec_in_global", C.c_int), ("profile", C.c_int), ("three_barrier_tcg", C.c_int)]
 
 
 class XmLogRec(C.Structure):
@@ -37,6 +37,21 @@ class XmStats(C.Structure):
                 ("ksplit", C.c_int), ("launches", C.c_int), ("phase_ms", C.c_double * 4)]
 
 
+class XmCertInfo(C.Structure):
+    _fields_ = [("certified", C.c_int), ("method", C.c_int), ("products", C.c_int), ("converged", C.c_int),
+                ("min_eig", C.c_double), ("dual", C.c_double), ("gap", C.c_double), ("residual", C.c_double), ("ms", C.c_double)]
+
+
+class XmSolveResult(C.Structure):
+    _fields_ = [("rank", C.c_int), ("status", C.c_int), ("n_solves", C.c_int), ("certified", C.c_int), ("cert_method", C.c_int),
+                ("tcg_iters_total", C.c_int), ("qy_products_total", C.c_int), ("cert_products_total", C.c_int),
+                ("primal", C.c_double), ("gradnorm", C.c_double), ("min_eig", C.c_double), ("dual", C.c_double), ("gap", C.c_double),
+                ("solve_ms_total", C.c_double), ("cert_ms_total", C.c_double)]
+
+
+CERT_METHODS = {"auto": 0, "dense": 1, "iterative": 2}
+MODES = {"full": 0, "rank3": 1, "rebuttle": 2}
+
 EXPORTS = [
     "xm_default_options", "xm_create", "xm_destroy", "xm_last_error", "xm_set_stream", "xm_set_q_dense",
     "xm_set_q_dense_dev", "xm_set_q_bsr", "xm_qy", "xm_qy_dev", "xm_trust_region", "xm_trust_region_dev",
@@ -44,6 +59,7 @@ EXPORTS = [
     "xm_bench_barrier", "xm_debug_trace",
     "xm_partition", "xm_comm_init", "xm_comm_connect", "xm_comm_connect_ptrs", "xm_comm_arena", "xm_comm_info", "xm_comm_reset", "xm_comm_disconnect",
     "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover", "xm_residuals", "xm_debug_counters",
+    "xm_certify_ex", "xm_op_diag_blocks", "xm_solve", "xm_create_matrix",
 ]
 XM_IPC_HANDLE_BYTES = 64
 XM_MAX_WORLD = 8
@@ -102,6 +118,10 @@ def load(path: str | None = None):
     lib.xm_set_q_dense_slab_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]
     lib.xm_recover.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp, ip]
     lib.xm_residuals.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.xm_certify_ex.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, C.c_int, vp, C.POINTER(XmCertInfo)]
+    lib.xm_op_diag_blocks.argtypes = [vp, vp]
+    lib.xm_solve.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp, vp, C.POINTER(XmSolveResult)]
+    lib.xm_create_matrix.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("xm_default_options", "xm_last_error", "xm_comm_arena"):
@@ -148,14 +168,14 @@ class Handle:
 
     def __init__(self, device: int = 0, grid_ctas: int = 0, ksplit: int = 0, replicate_stale_sr: bool = True,
                  verbose: bool = False, max_outer: int = 1000, max_inner: int = 1000, qy_variant: int = 0,
-                 vec_in_global: bool = False, profile: bool = False):
+                 vec_in_global: bool = False, profile: bool = False, three_barrier_tcg: bool = False):
         self.lib = load()
         opt = XmOptions()
         self.lib.xm_default_options(C.byref(opt))
         opt.device = device; opt.grid_ctas = grid_ctas; opt.ksplit = ksplit
         opt.replicate_stale_sr = int(replicate_stale_sr); opt.verbose = int(verbose)
         opt.max_outer = max_outer; opt.max_inner = max_inner; opt.qy_variant = qy_variant
-        opt.vec_in_global = int(vec_in_global); opt.profile = int(profile)
+        opt.vec_in_global = int(vec_in_global); opt.profile = int(profile); opt.three_barrier_tcg = int(three_barrier_tcg)
         self._h = C.c_void_p()
         rc = self.lib.xm_create(C.byref(self._h), C.byref(opt))
         if rc != 0:
@@ -362,9 +382,46 @@ class Handle:
                                           _ptr(t), _ptr(p), _ptr(err)), "xm_residuals")
         return err
 
-    def certify(self, R, s, lam, primal):
+    def certify(self, R, s, lam, primal, method: str = "auto"):
+        """xm_certify_ex: method "auto" | "dense" (cuSOLVER syevd on the assembled dual slack) | "iterative" (block Davidson on the
+        Q.Y operator; block-CSR / communicator capable)."""
         R = _f64(R); s = _f64(s)
-        v = np.empty(R.shape[0]); me = C.c_double(); du = C.c_double(); gap = C.c_double(); cert = C.c_int()
-        self._check(self.lib.xm_certify(self._h, R.shape[1], _ptr(R), _ptr(s), lam, primal, _ptr(v), C.byref(me), C.byref(du),
-                                        C.byref(gap), C.byref(cert)), "xm_certify")
-        return dict(certified=bool(cert.value), min_eig=me.value, dual=du.value, gap=gap.value, v=v)
+        v = np.empty(R.shape[0]); ci = XmCertInfo()
+        self._check(self.lib.xm_certify_ex(self._h, R.shape[1], _ptr(R), _ptr(s), lam, primal, CERT_METHODS[method], _ptr(v), C.byref(ci)),
+                    "xm_certify_ex")
+        return dict(certified=bool(ci.certified), min_eig=ci.min_eig, dual=ci.dual, gap=ci.gap, v=v,
+                    method={1: "dense", 2: "iterative"}.get(ci.method, str(ci.method)), products=ci.products, converged=bool(ci.converged),
+                    residual=ci.residual, ms=ci.ms)
+
+    def diag_blocks(self):
+        out = np.empty((self.N, 3, 3))
+        self._check(self.lib.xm_op_diag_blocks(self._h, _ptr(out)), "xm_op_diag_blocks")
+        return out
+
+    def solve(self, max_rank: int, tol: float, lam: float, max_time: float = 1000.0, mode: str = "full", s_init=None, cert_method: str = "auto"):
+        """xm_solve: the reference's rank staircase (solve / solve_rank3 / solve_rebuttle) on the handle's operator."""
+        N = self.N
+        cap = max(3, min(int(max_rank), XM_MAX_RANK))
+        R = np.zeros((3 * N, cap), order="F"); s = np.empty(N); res = XmSolveResult()
+        si = _f64(np.asarray(s_init).reshape(-1)) if s_init is not None else None
+        self._check(self.lib.xm_solve(self._h, MODES[mode], int(max_rank), tol, lam, max_time, _ptr(si) if si is not None else None,
+                                      CERT_METHODS[cert_method], _ptr(R), _ptr(s), C.byref(res)), "xm_solve")
+        out = {f[0]: getattr(res, f[0]) for f in XmSolveResult._fields_}
+        out["R"] = np.asfortranarray(R[:, :res.rank]); out["s"] = s
+        out["certificate_method"] = {1: "dense", 2: "iterative"}.get(res.cert_method, "none")
+        return out
+
+    def create_matrix(self, n_cameras: int, n_landmarks: int, cam, lm, w, pts, want_q: bool = True, want_abar: bool = False):
+        """xm_create_matrix: Q (and Abar) from observations, assembled on the device; the result becomes the handle's operator.
+        cam, lm: 0-based.  Returns (Q or None, Abar or None, assemble_ms)."""
+        cam = np.ascontiguousarray(cam, dtype=np.int32); lm = np.ascontiguousarray(lm, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float64); pts = np.ascontiguousarray(pts, dtype=np.float64)
+        n3 = 3 * n_cameras
+        Q = np.empty((n3, n3), order="F") if want_q else None
+        A = np.empty((n_cameras + n_landmarks - 1, n3), order="F") if want_abar else None
+        ms = C.c_double()
+        self._check(self.lib.xm_create_matrix(self._h, n_cameras, n_landmarks, cam.size, _ptr(cam), _ptr(lm), _ptr(w), _ptr(pts),
+                                              _ptr(Q) if Q is not None else None, _ptr(A) if A is not None else None, C.byref(ms)), "xm_create_matrix")
+        self.N = n_cameras
+        self.is_bsr = False
+        return Q, A, ms.value

@@ -54,7 +54,7 @@ extern "C" void xm_default_options(xm_options* o) {
     if (!o) return;
     memset(o, 0, sizeof(*o));
     o->device = 0; o->grid_ctas = 0; o->ksplit = 0; o->replicate_stale_sr = 1; o->verbose = 0;
-    o->max_outer = 1000; o->max_inner = 1000; o->qy_variant = 0; o->vec_in_global = 0; o->profile = 0;
+    o->max_outer = 1000; o->max_inner = 1000; o->qy_variant = 0; o->vec_in_global = 0; o->profile = 0; o->three_barrier_tcg = 0;
 }
 
 extern "C" const char* xm_last_error(const xm_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -459,8 +459,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.partials = (double*)q;
     d.N = (int)N; d.r = r; d.n3 = (int)n3; d.ldq = (int)ldq;
     d.x_cam_major = h->is_bsr ? 1 : 0;
-    d.e_rec = 0;
-    if (const char* e = getenv("XM_TUNE_EREC")) d.e_rec = atoi(e) ? 1 : 0;                        // EXPERIMENT: two-barrier tCG iteration
+    d.e_rec = h->opt.three_barrier_tcg ? 0 : 1;           // two-barrier tCG iteration (E recurrence) unless the caller asks for the reference's order
+    if (const char* e = getenv("XM_TUNE_EREC")) d.e_rec = atoi(e) ? 1 : 0;                        // A/B hook
     d.bsr_stage = 0; d.bsr_k8 = 0;          // measured best on B200 (profiles/r01_bsr_qy.md): bulk-TMA chunks, 4 gathers per sub-warp
     if (const char* e = getenv("XM_TUNE_BSR")) { const int v = atoi(e); d.bsr_stage = v & 1; d.bsr_k8 = (v >> 1) & 1; }      // A/B hook
     d.Q = h->is_bsr ? nullptr : h->Qp;
@@ -575,6 +575,7 @@ static int prepare(xm_handle* h, int r, Plan* plan) {
 static int check_abort(xm_handle* h) {
     int ab = 0;
     const int* flag = h->world > 1 ? (const int*)(h->arena + h->off_abort) : h->d_abort;
+    XM_CUDA(h, cudaStreamSynchronize(h->stream));
     XM_CUDA(h, cudaMemcpyAsync(&ab, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     XM_CUDA(h, cudaStreamSynchronize(h->stream));
     if (ab) { h->err = "device grid barrier timed out"; if (h->world > 1) h->comm_broken = true; return XM_ESYNC; }
@@ -619,6 +620,7 @@ static int qy_common(xm_handle* h, int r, double alpha, const double* X, double*
     const OutBind ob = bind_out(h, d, dev_ptrs ? out : h->io_Rout, h->io_sout);
     XM_CUDA(h, launch_ops(h, d, 0, p, h->stream));
     h->launches++;
+    if (!dev_ptrs) XM_CUDA(h, cudaStreamSynchronize(h->stream));      // see tr_common: never block inside a pageable copy behind a kernel
     if (!dev_ptrs || ob.R != out)
         XM_CUDA(h, cudaMemcpyAsync(out, ob.R, (size_t)d.n3 * r * sizeof(double), dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
     if (!dev_ptrs || h->world > 1) return check_abort(h);     // synchronises
@@ -743,6 +745,11 @@ static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, do
     XM_CUDA(h, launch_solve(h, d, p, h->stream));
     XM_CUDA(h, cudaEventRecord(e1, h->stream));
     h->launches++;
+    // Host (pageable) destinations: wait for the kernel with a plain stream synchronisation FIRST.  A pageable device-to-host copy
+    // blocks inside the driver until the kernel ahead of it has finished; when two members of a communicator share one device
+    // (one context: the loop-back team of the single-GPU test suite) that blocked call keeps the peer's thread from launching its
+    // own kernel — the two persistent kernels would wait for each other until the watchdog fires.
+    if (!dev_ptrs) XM_CUDA(h, cudaStreamSynchronize(h->stream));
     if (!dev_ptrs || ob.R != R_out) {
         const cudaMemcpyKind kout = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
         XM_CUDA(h, cudaMemcpyAsync(R_out, ob.R, bR, kout, h->stream));
@@ -800,6 +807,7 @@ static int op_common(xm_handle* h, int r, int opcode, const double* R, const dou
     const OutBind ob = bind_out(h, d, h->io_Rout, h->io_sout);
     XM_CUDA(h, launch_ops(h, d, opcode, p, h->stream));
     h->launches++;
+    XM_CUDA(h, cudaStreamSynchronize(h->stream));                      // see tr_common
     if (outR) XM_CUDA(h, cudaMemcpyAsync(outR, ob.R, bR, cudaMemcpyDeviceToHost, h->stream));
     if (outS) XM_CUDA(h, cudaMemcpyAsync(outS, ob.s, bS, cudaMemcpyDeviceToHost, h->stream));
     if (out_scalar) XM_CUDA(h, cudaMemcpyAsync(out_scalar, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -821,6 +829,31 @@ extern "C" int xm_op_retract(xm_handle* h, int r, const double* R, const double*
                              double lr, double* Rn, double* sn) {
     if (!etaR || !etas) return XM_EINVAL;
     return op_common(h, r, 4, R, s, 0.0, etaR, etas, lr, Rn, sn, nullptr);
+}
+
+// 3x3 diagonal blocks of the operator (N x 9 doubles, row-major per block) into a device buffer; collective on a communicator
+extern "C" int xm_op_diag_blocks_dev(xm_handle* h, double* out9N_dev) {
+    Plan p;
+    int rc = prepare(h, 3, &p);
+    if (rc) return rc;
+    if (!out9N_dev) return XM_EINVAL;
+    Dev d = h->dev;
+    const OutBind ob = bind_out(h, d, out9N_dev, h->io_sout);        // 9 N doubles fit the 3N x r (r >= 3) result copy of a communicator
+    XM_CUDA(h, launch_ops(h, d, 6, p, h->stream));
+    h->launches++;
+    if (ob.R != out9N_dev)
+        XM_CUDA(h, cudaMemcpyAsync(out9N_dev, ob.R, (size_t)h->N * 9 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return check_abort(h);
+}
+extern "C" int xm_op_diag_blocks(xm_handle* h, double* out9N) {
+    if (!h || !out9N || h->N <= 0) return XM_EINVAL;
+    XM_CUDA(h, cudaSetDevice(h->device));
+    double* tmp = nullptr;
+    XM_CUDA(h, cudaMalloc(&tmp, (size_t)h->N * 9 * sizeof(double)));
+    int rc = xm_op_diag_blocks_dev(h, tmp);
+    if (rc == XM_OK && cudaMemcpy(out9N, tmp, (size_t)h->N * 9 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); rc = XM_ECUDA; }
+    cudaFree(tmp);
+    return rc;
 }
 
 // debug: the 8 raw counters DevStats.dbg left on the device by the last launch (ns; meaning depends on the kernel/opcode)

@@ -482,6 +482,24 @@ __device__ __forceinline__ bool ops_body(Ctx<RP, NT, MG>& c, const Dev& d, const
         }
         return true;
     }
+    if (opcode == 6) {                 // the 3x3 diagonal blocks of the operator, 9 doubles per camera (row-major), into every rank's
+        XM_FOR_OWN_CAMERAS(c, i, valid) {   // output copy — the block-Jacobi preconditioner of the iterative certificate needs all of them
+            if (valid && c.j < 3) {
+                const int a = c.j;
+                double q[3] = {0.0, 0.0, 0.0};
+                if (PATH == 2) {
+                    for (int b = d.bsr_rowptr[i - d.cam0]; b < d.bsr_rowptr[i - d.cam0 + 1]; ++b)
+                        if (d.bsr_col[b] == i) { const double* blk = d.bsr_val + (size_t)b * 16 + 4 * a; q[0] = blk[0]; q[1] = blk[1]; q[2] = blk[2]; }
+                } else {
+                    const double* row = d.Q + (size_t)(3 * i + a - d.row0) * d.ldq + 3 * i;
+                    q[0] = row[0]; q[1] = row[1]; q[2] = row[2];
+                }
+#pragma unroll 1
+                for (int w = 0; w < c.world(); ++w) { double* o = d.outR_peer[w] + (size_t)i * 9 + 3 * a; o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; }
+            }
+        }
+        return true;
+    }
     phase_load_point(c, d.R0, d.s0);
     if (opcode == 4) {
         // direction arrives in wire layout: convert into V / vs first

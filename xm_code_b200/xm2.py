@@ -116,9 +116,8 @@ def refine(edges, landmarks, weights, rgbs, N, M, output_path, solver=None, hand
         return binio.load_matrix_from_bin(output_path + "/" + name)
 
     edges, landmarks, weights, rgbs, frame_map = check_landmarks(edges, landmarks, weights, rgbs, N, M)
-    N = int(edges[:, 0].max())
     create_matrix(weights, edges, landmarks, output_path)
-    lam = edges.shape[0] / N
+    lam = edges.shape[0] / N                 # the reference divides by the PRE-clean-up frame count (3_test_colmap_glomap.py:280-284)
     solver.solve(output_path, max_rank, tol, lam, max_time)
     R_real, s_real, p_est, t_est = recover_XM(load("Q.bin"), load("R.bin"), load("s.bin"), load("Abar.bin"), lam, handle=handle)
     errors = observation_errors(edges, landmarks, weights, R_real, s_real, t_est, p_est, handle=handle)
@@ -127,10 +126,10 @@ def refine(edges, landmarks, weights, rgbs, N, M, output_path, solver=None, hand
     edges = np.delete(edges, rm, axis=0); weights = np.delete(weights, rm); rgbs = np.delete(rgbs, rm, axis=0)
     landmarks = np.delete(landmarks, rm, axis=0)
     # second run
+    N = int(np.asarray(s_real).reshape(-1).shape[0])       # first-pass camera count (:296): also the divisor of the second lam (:341)
     M = int(p_est.shape[1])
     edges, landmarks, weights, rgbs, fmap2 = check_landmarks(edges, landmarks, weights, rgbs, N, M)
     frame_map = _compose(frame_map, fmap2)
-    N = int(edges[:, 0].max())
     create_matrix(weights, edges, landmarks, output_path)
     lam = 0.0
     solver.solve_rank3(output_path, 3, tol, lam, max_time)
@@ -139,9 +138,9 @@ def refine(edges, landmarks, weights, rgbs, N, M, output_path, solver=None, hand
     if np.abs(s_avg - 1) > 2 * s_std or np.sum(s < 0.1) > 10:      # decide whether the scale regulariser is needed (:338-344)
         print("s is too small, run again")
         lam = edges.shape[0] / N
+        solver.solve(output_path, max_rank, tol, lam, max_time)        # only in this branch (:339-342); otherwise the rank-3 result stands
     else:
         print("s is good")
-    solver.solve(output_path, max_rank, tol, lam, max_time)
     R_real, s_real, p_est, t_est = recover_XM(load("Q.bin"), load("R.bin"), load("s.bin"), load("Abar.bin"), lam, handle=handle)
     return dict(R=R_real, s=s_real, p=p_est, t=t_est, edges=edges, landmarks=landmarks, weights=weights, rgbs=rgbs,
                 frame_map=frame_map, errors=errors, lam=lam)
