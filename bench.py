@@ -131,16 +131,25 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def source_hash():
+    """Hash of the library's sources (csrc + the C header): identifies the build an ncu capture belongs to."""
+    import hashlib
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "xm_code_b200", "csrc")
+    for f in sorted(os.listdir(d)) + ["../../include/xm_b200.h"]:
+        if f.endswith((".cu", ".cuh", ".h")):
+            hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()[:16]
+
+
 def measured_traffic(n_cameras):
     """dram bytes per Q.Y product of the persistent solve kernel from an ncu capture of THIS build (tools/ncu_traffic.py writes
-    profiles/r02_solve_traffic.json with the library's hash); None when there is no capture for this workload / build."""
+    profiles/r02_solve_traffic.json with the hash of the library's sources); None when there is no capture for this workload / build."""
     try:
-        import hashlib
         t = json.load(open(os.path.join(ROOT, "profiles", "r02_solve_traffic.json")))
-        lib = os.path.join(ROOT, "xm_code_b200", "libxm_b200.so")
-        sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
+        sha = source_hash()
         for rec in t["captures"]:
-            if rec["cameras"] == n_cameras and rec["lib_sha16"] == sha:
+            if rec["cameras"] == n_cameras and rec["src_sha16"] == sha:
                 return rec["dram_bytes_per_product"], f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one solve launch of this build ({rec['source']}), per product"
     except Exception:
         pass

@@ -129,6 +129,14 @@ int  xm_comm_disconnect(xm_handle* h);  /* unmap the peers' arenas; every rank c
 void* xm_comm_arena(xm_handle* h);
 int  xm_comm_info(const xm_handle* h, int* rank, int* world, int* ctas_per_rank, int* cam_lo, int* cam_hi);
 int  xm_comm_reset(xm_handle* h);   /* after XM_ESYNC; host-side barrier across ranks required before and after */
+/* Boundary-only operand exchange of the CURRENT block-CSR operator on a communicator: n_need = remote cameras this rank unpacks per
+ * exchange, n_sent = (camera, peer) pairs it pushes, n_remote = cameras owned by the other ranks (what a dense operator's full
+ * all-gather moves).  xm_set_q_bsr builds the tables from the whole matrix every rank passes in. */
+int  xm_comm_halo(const xm_handle* h, int* n_need, long long* n_sent, int* n_remote);
+/* Reverse Cuthill-McKee camera order of a block-CSR view graph (perm_out[new] = old; pure host function, no GPU).  Ranks own
+ * CONTIGUOUS camera ranges, so the order decides the cut: permute the matrix (and R, s) with it before xm_set_q_bsr and a view
+ * graph with locality exchanges a few percent of the operand rows instead of all of them. */
+int  xm_rcm_order(int nb, const int* rowptr, const int* colidx, int* perm_out);
 /* Rows [row0, row0 + nrows) of Q only: q_slab points at element (row0, 0) of a column-major matrix with leading dimension
  * ld >= nrows (ld = n3 when it is a view into the full matrix).  Must equal the rank's range 3*cam_lo .. 3*cam_hi. */
 int  xm_set_q_dense_slab(xm_handle* h, int n3, int row0, int nrows, const double* q_slab, int64_t ld);

@@ -279,3 +279,41 @@ def test_staircase_on_a_communicator(team_factory):
         assert out["certificate_method"] == "iterative"
         assert out["rank"] == ref["rank"] and out["status"] == ref["status"]
         assert abs(out["primal"] - ref["trace"][-1].primal) <= 1e-5 * abs(ref["trace"][-1].primal)
+
+
+def test_boundary_only_exchange_on_a_banded_view_graph(team_factory):
+    """Block-CSR solve on a communicator whose view graph has locality (banded: a video-like capture), cameras shuffled and then
+    put back into a band by the library's RCM order: every rank unpacks only a thin halo instead of all remote cameras, and
+    the result matches the oracle (and the full exchange) — SURVEY.md §8e "graph cut + boundary allgather"."""
+    from xm_code_b200 import problems, capi, dist as xdist
+    N = 600
+    rowptr, col, vals = problems.banded_bsr(N, half_bandwidth=5, seed=4)
+    rng = np.random.default_rng(8)
+    shuffle = rng.permutation(N)
+    rp_s, col_s, vals_s = xdist.permute_bsr(rowptr, col, vals, shuffle)            # how the cameras arrive: no locality in the order
+    perm = capi.rcm_order(rp_s, col_s)
+    rp, cc, vv = xdist.permute_bsr(rp_s, col_s, vals_s, perm)                      # banded again
+    Q = problems.bsr_to_dense(rp, cc, vv)
+    r = 4
+    Y0 = xo.mgs_rows(rng.standard_normal((N, 3, r)))
+    s0 = np.concatenate([[1.0], rng.uniform(0.8, 1.25, N - 1)])
+    ref = xo.trust_region(Q, Y0, s0, 0.0, 1e-8)
+    t = team_factory(N, r)
+    t.call("set_q_bsr", rp, cc, vv, 3)
+    for hs in t.call("comm_halo"):
+        assert 0 < hs["need"] <= 0.05 * hs["remote"] + 12, hs                      # a few boundary cameras, not all remote ones
+    res = t.call("trust_region", xo.from_blocks(Y0), s0, 0.0, 1e-8)
+    for got in res:
+        assert abs(got.primal - ref.primal) <= 1e-8 * abs(ref.primal)
+        np.testing.assert_allclose(got.s, ref.s, atol=1e-6, rtol=0)
+    X = rng.standard_normal((3 * N, r))
+    for got in t.call("qy", X, 1.0):
+        assert rel(got, Q @ X) < TOL
+    # the shuffled order on the same team size: (almost) every remote camera is needed — the partition is not a graph cut there
+    t2 = team_factory(N, r)
+    t2.call("set_q_bsr", rp_s, col_s, vals_s, 3)
+    for hs in t2.call("comm_halo"):
+        assert hs["need"] > 0.5 * hs["remote"], hs
+    Qs = problems.bsr_to_dense(rp_s, col_s, vals_s)
+    for got in t2.call("trust_region", xo.from_blocks(Y0), s0, 0.0, 1e-8):
+        assert abs(got.primal - xo.trust_region(Qs, Y0, s0, 0.0, 1e-8).primal) <= 1e-7 * abs(got.primal)

@@ -25,8 +25,9 @@ for r in rows[1:]:
     vals[r[iname]] = v * scale
     kern = r[ikern]
 total = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-lib = os.path.join(ROOT, "xm_code_b200", "libxm_b200.so")
-rec = {"cameras": cameras, "lib_sha16": hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16], "kernel": kern[:120], "products": products,
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+rec = {"cameras": cameras, "src_sha16": bench.source_hash(), "kernel": kern[:120], "products": products,
        "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"], "dram_bytes_per_product": total / products,
        "algorithmic_bytes_per_product": 72.0 * cameras ** 2 + 48.0 * cameras * 3, "kernel_ms_under_ncu": vals.get("gpu__time_duration.sum", 0) / 1e6,
        "source": os.path.basename(csv_path)}
@@ -35,6 +36,6 @@ try:
     doc = json.load(open(out_path))
 except Exception:
     doc = {"captures": []}
-doc["captures"] = [c for c in doc["captures"] if not (c["cameras"] == cameras and c["lib_sha16"] == rec["lib_sha16"])] + [rec]
+doc["captures"] = [c for c in doc["captures"] if not (c["cameras"] == cameras and c.get("src_sha16") == rec["src_sha16"])] + [rec]
 json.dump(doc, open(out_path, "w"), indent=1)
 print(json.dumps(rec))

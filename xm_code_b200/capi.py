@@ -59,7 +59,7 @@ EXPORTS = [
     "xm_bench_barrier", "xm_debug_trace",
     "xm_partition", "xm_comm_init", "xm_comm_connect", "xm_comm_connect_ptrs", "xm_comm_arena", "xm_comm_info", "xm_comm_reset", "xm_comm_disconnect",
     "xm_set_q_dense_slab", "xm_set_q_dense_slab_dev", "xm_recover", "xm_residuals", "xm_debug_counters",
-    "xm_certify_ex", "xm_op_diag_blocks", "xm_solve", "xm_create_matrix",
+    "xm_certify_ex", "xm_op_diag_blocks", "xm_solve", "xm_create_matrix", "xm_comm_halo", "xm_rcm_order",
 ]
 XM_IPC_HANDLE_BYTES = 64
 XM_MAX_WORLD = 8
@@ -122,6 +122,8 @@ def load(path: str | None = None):
     lib.xm_op_diag_blocks.argtypes = [vp, vp]
     lib.xm_solve.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp, vp, C.POINTER(XmSolveResult)]
     lib.xm_create_matrix.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, dp]
+    lib.xm_comm_halo.argtypes = [vp, ip, C.POINTER(C.c_longlong), ip]
+    lib.xm_rcm_order.argtypes = [C.c_int, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("xm_default_options", "xm_last_error", "xm_comm_arena"):
@@ -143,6 +145,17 @@ def partition(n_cameras: int, world: int, ctas_per_rank: int, rank: int):
     if rc != 0:
         raise XmError(f"xm_partition: {ERRORS.get(rc, rc)}")
     return lo.value, hi.value
+
+
+def rcm_order(rowptr, colidx) -> np.ndarray:
+    """xm_rcm_order: reverse Cuthill-McKee camera order of a block-CSR view graph (perm[new] = old); host only."""
+    lib = load()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    perm = np.empty(rowptr.size - 1, dtype=np.int32)
+    rc = lib.xm_rcm_order(rowptr.size - 1, rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p), perm.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise XmError(f"xm_rcm_order: {ERRORS.get(rc, rc)}")
+    return perm.astype(np.int64)
 
 
 def _f64(a, order="F"):
@@ -221,6 +234,12 @@ class Handle:
         v = [C.c_int() for _ in range(5)]
         self._check(self.lib.xm_comm_info(self._h, *[C.byref(x) for x in v]), "xm_comm_info")
         return dict(zip(("rank", "world", "ctas_per_rank", "cam_lo", "cam_hi"), (x.value for x in v)))
+
+    def comm_halo(self) -> dict:
+        """Boundary-only exchange of the current block-CSR operator: cameras unpacked / (camera, peer) pairs pushed per exchange."""
+        a, b, c = C.c_int(), C.c_longlong(), C.c_int()
+        self._check(self.lib.xm_comm_halo(self._h, C.byref(a), C.byref(b), C.byref(c)), "xm_comm_halo")
+        return dict(need=a.value, sent=b.value, remote=c.value)
 
     def comm_disconnect(self):
         self._check(self.lib.xm_comm_disconnect(self._h), "xm_comm_disconnect")

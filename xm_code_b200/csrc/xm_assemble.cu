@@ -19,6 +19,11 @@
 #include <string>
 #include <algorithm>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <chrono>
+
+int xm_internal_libs(xm_handle* h, void** cublas_out, void** cusolver_out);    // xm_capi.cu
 
 namespace {
 
@@ -118,10 +123,7 @@ struct Bufs {
     ~Bufs() { for (void* q : p) cudaFree(q); }
     template <class T> T* get(size_t n) { void* q = nullptr; if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; } p.push_back(q); return (T*)q; }
 };
-struct Libs {
-    cublasHandle_t cb = nullptr; cusolverDnHandle_t cs = nullptr;
-    ~Libs() { if (cb) cublasDestroy(cb); if (cs) cusolverDnDestroy(cs); }
-};
+struct Libs { cublasHandle_t cb = nullptr; cusolverDnHandle_t cs = nullptr; };      // views of the handle's cached library handles
 
 // group the observation indices by key (counting sort: stable, original order inside a group)
 void group_by(const int* key, int64_t n, int nkeys, std::vector<int>& ptr, std::vector<int>& idx) {
@@ -139,6 +141,7 @@ void group_by(const int* key, int64_t n, int nkeys, std::vector<int>& ptr, std::
 
 extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, int64_t n_obs, const int* cam, const int* lm,
                                 const double* w, const double* pts, double* Q_out, double* Abar_out, double* assemble_ms_out) {
+    XmRange nvtx_range("xm_create_matrix");
     if (!h || !cam || !lm || !w || !pts || n_cameras < 2 || n_landmarks < 1 || n_obs < 1 || n_obs > 2000000000LL) return XM_EINVAL;
     if (h->world > 1) { h->err = "xm_create_matrix assembles on one GPU (attach the communicator afterwards and upload the slabs)"; return XM_EUNSUPPORTED; }
     const int N = n_cameras, M = n_landmarks, n3 = 3 * N, ldq = (n3 + 63) / 64 * 64;
@@ -148,6 +151,7 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     group_by(lm, n_obs, M, lm_ptr, lm_obs);
     group_by(cam, n_obs, N, cam_ptr, cam_obs);
     for (int k = 0; k < M; ++k) if (lm_ptr[k + 1] == lm_ptr[k]) { h->err = "every landmark needs at least one observation"; return XM_EINVAL; }
+    const auto t_wall0 = std::chrono::steady_clock::now();
     ASM_CUDA(cudaSetDevice(h->device));
     // the operator buffer of the handle receives the result
     if (h->Qp_cap < (size_t)n3 * ldq * sizeof(double) || !h->Qp) {
@@ -178,15 +182,18 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     ASM_CUDA(cudaMemsetAsync(h->Qp, 0, (size_t)n3 * ldq * sizeof(double), st));
     ASM_CUDA(cudaMemsetAsync(Sc, 0, (size_t)N * N * sizeof(double), st));
     ASM_CUDA(cudaMemsetAsync(B, 0, (size_t)n3 * N * sizeof(double), st));
+    const bool trace = getenv("XM_ASM_TRACE") != nullptr;
+    auto mark = [&](const char* what) { if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[xm_create_matrix] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wall0).count()); } };
+    mark("uploads + memsets");
     const Obs o{d_cam, d_lm, d_w, d_pt};
     landmark_degree_kernel<<<(M + 255) / 256, 256, 0, st>>>(o, d_lm_ptr, d_lm_obs, M, dl);
     camera_terms_kernel<<<(N + 127) / 128, 128, 0, st>>>(o, d_cam_ptr, d_cam_obs, N, n3, ldq, h->Qp, B, Sc);
     landmark_pairs_kernel<<<(unsigned)(((long long)M * 32 + 255) / 256), 256, 0, st>>>(o, d_lm_ptr, d_lm_obs, dl, M, N, n3, ldq, h->Qp, B, Sc);
     ASM_CUDA(cudaGetLastError());
     h->launches += 3;
+    mark("elimination kernels");
     // (N-1) x (N-1) Cholesky of the reduced camera Laplacian, Y = Bb L^-T, Q -= Y Y^T (lower triangle), mirror
-    if (cublasCreate(&lib.cb) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&lib.cs) != CUSOLVER_STATUS_SUCCESS) { h->err = "cublasCreate / cusolverDnCreate failed"; return XM_ECUDA; }
-    cublasSetStream(lib.cb, st); cusolverDnSetStream(lib.cs, st);
+    { const int lrc = xm_internal_libs(h, (void**)&lib.cb, (void**)&lib.cs); if (lrc) return lrc; }
     double* Scb = Sc + (size_t)N + 1;                              // Sc[1:, 1:], leading dimension N
     double* Bb = B + (size_t)n3;                                   // B[:, 1:]
     int lwork = 0;
@@ -197,6 +204,7 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     int hinfo = 0;
     ASM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
     ASM_CUDA(cudaStreamSynchronize(st));
+    mark("potrf");
     if (hinfo != 0) { h->err = "the reduced camera Laplacian is not positive definite (the camera-landmark graph is disconnected?)"; return XM_EINVAL; }
     const double one = 1.0, mone = -1.0;
     if (cublasDtrsm(lib.cb, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n3, N - 1, &one, Scb, N, Bb, n3) != CUBLAS_STATUS_SUCCESS) { h->err = "cublasDtrsm"; return XM_ECUDA; }
@@ -205,6 +213,7 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     ASM_CUDA(cudaGetLastError());
     h->launches += 1;
     ASM_CUDA(cudaEventRecord(ev1, st));
+    mark("trsm + syrk + mirror");
     if (Abar_out) {
         // Zt = Y L^-1 = Bb Scb^-1 ; a_t = -Zt^T ; b_p from the observations and a_t
         const long long rows = (long long)N + M - 1;
@@ -220,6 +229,7 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     if (Q_out)
         ASM_CUDA(cudaMemcpy2DAsync(Q_out, (size_t)n3 * sizeof(double), h->Qp, (size_t)ldq * sizeof(double), (size_t)n3 * sizeof(double), n3, cudaMemcpyDeviceToHost, st));
     ASM_CUDA(cudaStreamSynchronize(st));
+    mark("Abar + copies out");
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);

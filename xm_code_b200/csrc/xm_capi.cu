@@ -2,6 +2,8 @@
 // There is no CPU fallback anywhere in this file: without an sm_100 device every entry point fails with XM_ENOGPU.
 #include "xm_host.h"
 #include "xm_solve.cuh"
+#include <cublas_v2.h>
+#include <cusolverDn.h>
 
 #include <cstddef>
 #include <cstdio>
@@ -98,9 +100,11 @@ extern "C" int xm_create(xm_handle** out, const xm_options* opt) {
 extern "C" int xm_destroy(xm_handle* h) {
     if (!h) return XM_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->Qp); cudaFree(h->Qstage); cudaFree(h->bsr_rowptr); cudaFree(h->bsr_col); cudaFree(h->bsr_val);
+    cudaFree(h->Qp); cudaFree(h->Qstage); cudaFree(h->bsr_rowptr); cudaFree(h->bsr_col); cudaFree(h->bsr_val); cudaFree(h->d_peer_mask); cudaFree(h->d_need_cams);
     cudaFree(h->ws); cudaFree(h->d_stats); cudaFree(h->d_log); cudaFree(h->d_bar); cudaFree(h->d_abort); cudaFree(h->d_scalar);
     cudaFree(h->io_R0); cudaFree(h->io_s0); cudaFree(h->io_v); cudaFree(h->io_Rout); cudaFree(h->io_sout); cudaFree(h->io_P); cudaFree(h->io_ps);
+    if (h->cublas) cublasDestroy((cublasHandle_t)h->cublas);
+    if (h->cusolver) cusolverDnDestroy((cusolverDnHandle_t)h->cusolver);
     cudaFreeHost(h->h_stats); cudaFreeHost(h->h_log);
     for (int w = 0; w < kMaxWorld; ++w) if (h->peer_ipc[w] && h->peer_arena[w]) cudaIpcCloseMemHandle(h->peer_arena[w]);
     cudaFree(h->arena);
@@ -112,6 +116,27 @@ extern "C" int xm_destroy(xm_handle* h) {
 extern "C" int xm_set_stream(xm_handle* h, void* s) {
     if (!h) return XM_EINVAL;
     h->stream = (cudaStream_t)s;
+    if (h->cublas) cublasSetStream((cublasHandle_t)h->cublas, h->stream);
+    if (h->cusolver) cusolverDnSetStream((cusolverDnHandle_t)h->cusolver, h->stream);
+    return XM_OK;
+}
+
+// the handle's cuBLAS / cuSOLVER handles (created on first use, bound to the handle's stream, destroyed with the handle)
+int xm_internal_libs(xm_handle* h, void** cublas_out, void** cusolver_out) {
+    if (!h->cublas) {
+        cublasHandle_t cb = nullptr;
+        if (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS) { h->err = "cublasCreate failed"; return XM_ECUDA; }
+        h->cublas = cb;
+    }
+    if (!h->cusolver) {
+        cusolverDnHandle_t cs = nullptr;
+        if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) { h->err = "cusolverDnCreate failed"; return XM_ECUDA; }
+        h->cusolver = cs;
+    }
+    cublasSetStream((cublasHandle_t)h->cublas, h->stream);
+    cusolverDnSetStream((cusolverDnHandle_t)h->cusolver, h->stream);
+    if (cublas_out) *cublas_out = h->cublas;
+    if (cusolver_out) *cusolver_out = h->cusolver;
     return XM_OK;
 }
 
@@ -261,6 +286,7 @@ static void owned_cameras(const xm_handle* h, int N, int* c0, int* c1) {
 
 // q_slab: first element of row `row0` of the column-major n3-column matrix (leading dimension ld), nrows rows
 static int set_q_common(xm_handle* h, int n3, int row0, int nrows, const double* q_slab, int64_t ld, bool from_device) {
+    XmRange nvtx_range("xm_set_q_dense");
     if (!h || !q_slab || n3 <= 0 || n3 % 3 != 0 || ld < nrows || nrows <= 0) return XM_EINVAL;
     if (h->world > 1 && h->comm_N * 3 != n3) { h->err = "Q size differs from the communicator's camera count"; return XM_EINVAL; }
     int c0, c1;
@@ -344,6 +370,73 @@ extern "C" int xm_set_q_bsr(xm_handle* h, int nb, int bdim, const int* rowptr, c
     h->bsr_bdim = bdim; h->is_bsr = true;
     h->N = nb; h->n3 = 3 * nb; h->ldq = (h->n3 + 63) / 64 * 64;
     h->cam0 = c0; h->cam1 = c1;
+    cudaFree(h->d_peer_mask); cudaFree(h->d_need_cams);
+    h->d_peer_mask = nullptr; h->d_need_cams = nullptr; h->n_need = 0; h->halo_sent = 0;
+    if (h->world > 1) {
+        // boundary-only exchange: which ranks reference which cameras (the caller passed the whole matrix, so every rank can
+        // work out the same table); this rank's own list of remote cameras to unpack
+        std::vector<unsigned char> mask((size_t)nb, 0);
+        std::vector<int> need;
+        for (int w = 0; w < h->world; ++w) {
+            int lo, hi;
+            xm_partition(nb, h->world, h->comm_G, w, &lo, &hi);
+            for (long long b = rowptr[lo]; b < rowptr[hi]; ++b) {
+                const int c = colidx[b];
+                if (c < 0 || c >= nb) { h->err = "block column index out of range"; return XM_EINVAL; }
+                mask[c] |= (unsigned char)(1u << w);
+            }
+        }
+        for (int c = 0; c < nb; ++c) {
+            if ((c < c0 || c >= c1) && ((mask[c] >> h->rank) & 1u)) need.push_back(c);
+            if (c >= c0 && c < c1) for (int w = 0; w < h->world; ++w) if (w != h->rank && ((mask[c] >> w) & 1u)) h->halo_sent++;
+        }
+        h->n_need = (int)need.size();
+        XM_CUDA(h, cudaMalloc(&h->d_peer_mask, (size_t)nb));
+        XM_CUDA(h, cudaMalloc(&h->d_need_cams, sizeof(int) * std::max<size_t>(need.size(), 1)));
+        XM_CUDA(h, cudaMemcpy(h->d_peer_mask, mask.data(), (size_t)nb, cudaMemcpyHostToDevice));
+        if (!need.empty()) XM_CUDA(h, cudaMemcpy(h->d_need_cams, need.data(), sizeof(int) * need.size(), cudaMemcpyHostToDevice));
+    }
+    return XM_OK;
+}
+
+// boundary-only exchange of the current block-CSR operator: remote cameras this rank unpacks per exchange, (camera, peer) pairs it
+// pushes, and the remote cameras there are (what the full all-gather of a dense operator moves)
+extern "C" int xm_comm_halo(const xm_handle* h, int* n_need, long long* n_sent, int* n_remote) {
+    if (!h) return XM_EINVAL;
+    const bool on = h->world > 1 && h->is_bsr && h->d_peer_mask;
+    if (n_need) *n_need = on ? h->n_need : (h->world > 1 ? h->N - (h->cam1 - h->cam0) : 0);
+    if (n_sent) *n_sent = on ? h->halo_sent : (long long)(h->cam1 - h->cam0) * (h->world - 1);
+    if (n_remote) *n_remote = h->world > 1 ? h->N - (h->cam1 - h->cam0) : 0;
+    return XM_OK;
+}
+
+// Reverse Cuthill-McKee order of the cameras of a block-CSR view graph ("simple BFS/RCM bands"): perm_out[new] = old.
+// The library partitions CONTIGUOUS camera ranges over the ranks, so the camera order decides the cut: after this ordering a view
+// graph with locality becomes banded and the boundary-only exchange moves a few percent of the rows.  Pure host function.
+extern "C" int xm_rcm_order(int nb, const int* rowptr, const int* colidx, int* perm_out) {
+    if (nb <= 0 || !rowptr || !colidx || !perm_out) return XM_EINVAL;
+    std::vector<int> deg(nb), order; std::vector<char> seen(nb, 0);
+    for (int i = 0; i < nb; ++i) deg[i] = rowptr[i + 1] - rowptr[i];
+    std::vector<int> by_deg(nb);
+    for (int i = 0; i < nb; ++i) by_deg[i] = i;
+    std::stable_sort(by_deg.begin(), by_deg.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+    order.reserve(nb);
+    std::vector<int> nbrs;
+    for (int s = 0; s < nb; ++s) {                       // one BFS per connected component, started at a minimum-degree camera
+        const int root = by_deg[s];
+        if (seen[root]) continue;
+        seen[root] = 1;
+        size_t head = order.size();
+        order.push_back(root);
+        while (head < order.size()) {
+            const int u = order[head++];
+            nbrs.clear();
+            for (int b = rowptr[u]; b < rowptr[u + 1]; ++b) { const int v = colidx[b]; if (v >= 0 && v < nb && !seen[v]) { seen[v] = 1; nbrs.push_back(v); } }
+            std::stable_sort(nbrs.begin(), nbrs.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+            order.insert(order.end(), nbrs.begin(), nbrs.end());
+        }
+    }
+    for (int k = 0; k < nb; ++k) perm_out[k] = order[nb - 1 - k];
     return XM_OK;
 }
 
@@ -374,7 +467,14 @@ static int make_map(xm_handle* h, CUtensorMap* m, const double* base, uint64_t c
 static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     Plan p{};
     p.RP = rank_pad(r);
-    p.NT = (p.RP <= 10 || h->is_bsr) ? 512 : 256;      // dense sweeps hold 3 x RP accumulators per lane; block-CSR holds 3
+    p.NT = (p.RP <= 10) ? 512 : 256;                   // dense sweeps hold 3 x RP accumulators per lane
+    if (h->is_bsr) {
+        // block-CSR holds 3 accumulators per lane whatever the rank; the operand gather is latency-bound, so resident warps
+        // matter more than registers: 1024 threads (32 warps, <= 64 registers, 16-block chunks, 2 gathers in flight per sub-warp)
+        // measured 8 / 21 / 23 % faster than 512 threads at r = 5 / 10 / 20 on ER-100k (profiles/r02_bsr_tune.txt)
+        p.NT = 1024;
+        if (const char* e = getenv("XM_TUNE_BSR_NT")) { if (atoi(e) == 512) p.NT = 512; }             // A/B hook
+    }
     p.NW = p.NT / 32;
     p.W = 4; while (p.W < r) p.W <<= 1;
     p.cpw = 32 / p.W;
@@ -406,7 +506,7 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.vec_smem = (h->opt.vec_in_global == 0 && p.vec_bytes <= 64 * 1024) ? 1 : 0;
     if (p.vec_smem) budget -= p.vec_bytes;
     p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
-    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * (kBsrChunk * 128 + 8);      // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
+    if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * ((p.NT == 1024 ? 16 : 32) * 128 + 8);      // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
     if (p.use_tma) {
         p.nbmax = std::min(p.CB, cpc);
         p.stage_doubles = (3 * p.nbmax + p.RP) * p.KC;   // operand area sized for the padded rank (consumers read RP rows)
@@ -461,8 +561,10 @@ static int carve(xm_handle* h, int r, const Plan& p) {
     d.x_cam_major = h->is_bsr ? 1 : 0;
     d.e_rec = h->opt.three_barrier_tcg ? 0 : 1;           // two-barrier tCG iteration (E recurrence) unless the caller asks for the reference's order
     if (const char* e = getenv("XM_TUNE_EREC")) d.e_rec = atoi(e) ? 1 : 0;                        // A/B hook
-    d.bsr_stage = 0; d.bsr_k8 = 0;          // measured best on B200 (profiles/r01_bsr_qy.md): bulk-TMA chunks, 4 gathers per sub-warp
-    if (const char* e = getenv("XM_TUNE_BSR")) { const int v = atoi(e); d.bsr_stage = v & 1; d.bsr_k8 = (v >> 1) & 1; }      // A/B hook
+    d.bsr_stage = 0;                        // measured best on B200 (profiles/r01_bsr_qy.md): bulk-TMA chunks
+    d.bsr_chunk = (p.NT == 1024) ? 16 : 32; d.bsr_k = (p.NT == 1024) ? 2 : 4;
+    if (const char* e = getenv("XM_TUNE_BSR")) { const int v = atoi(e); d.bsr_stage = v & 1; if ((v >> 1) & 1) d.bsr_k = 8; }      // A/B hook
+    if (const char* e = getenv("XM_TUNE_BSR_K")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) d.bsr_k = v; }
     d.Q = h->is_bsr ? nullptr : h->Qp;
     if (h->is_bsr) { d.bsr_rowptr = h->bsr_rowptr; d.bsr_col = h->bsr_col; d.bsr_val = h->bsr_val; d.bsr_bdim = h->bsr_bdim; }   // else null: dense
     d.G = p.G; d.NW = p.NW; d.KS = p.KS; d.CB = p.CB; d.W = p.W; d.cpw = p.cpw; d.NSW = p.NSW;
@@ -476,7 +578,8 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         d.nown = 3 * (h->cam1 - h->cam0);
         // protocol switch (like NCCL's LL vs Simple): tagged words double the bytes but need no fence; above ~2 MB per rank and
         // exchange the NVLink time of the extra bytes outweighs the 3.5 us fence
-        d.push_plain = ((size_t)d.nown * r * sizeof(double) * (h->world - 1) > (size_t)(2 << 20)) ? 1 : 0;
+        const size_t pushed_rows = (h->is_bsr && h->d_peer_mask) ? (size_t)3 * h->halo_sent : (size_t)d.nown * (h->world - 1);
+        d.push_plain = (pushed_rows * r * sizeof(double) > (size_t)(2 << 20)) ? 1 : 0;
         if (const char* e = getenv("XM_TUNE_PUSH")) d.push_plain = atoi(e) ? 1 : 0;                 // A/B hook
         for (int w = 0; w < h->world; ++w) {
             d.Xt_peer[w] = (double*)(h->peer_arena[w] + h->off_xt); d.ll_peer[w] = (unsigned long long*)(h->peer_arena[w] + h->off_ll);
@@ -485,6 +588,12 @@ static int carve(xm_handle* h, int r, const Plan& p) {
         }
     } else {
         d.Xt_peer[0] = d.Xt; d.abort_peer[0] = d.abort_flag;
+    }
+    if (h->world > 1 && h->is_bsr && h->d_peer_mask && !getenv("XM_TUNE_FULL_EXCHANGE")) { d.peer_mask = h->d_peer_mask; d.need_cams = h->d_need_cams; d.n_need = h->n_need; }
+    {
+        double scale = 1.0;       // compute-sanitizer / debugger runs are 10-100x slower: XM_WATCHDOG_SCALE stretches the abort deadline
+        if (const char* e = getenv("XM_WATCHDOG_SCALE")) scale = std::max(1.0, atof(e));
+        d.watchdog_ns = (unsigned long long)((h->world > 1 ? 30e9 : 4e9) * scale);    // multi-GPU: generous — the ranks' hosts launch independently
     }
     d.vec_smem = p.vec_smem; d.cpc_max = p.cpc; d.profile = h->opt.profile;
     d.nprod = p.nprod; d.NWC = p.NWC;
@@ -595,6 +704,7 @@ static OutBind bind_out(xm_handle* h, Dev& d, double* R_dev, double* s_dev) {
 
 // ------------------------------------------------------------------------------------------------ Q.Y
 static int qy_common(xm_handle* h, int r, double alpha, const double* X, double* out, bool dev_ptrs) {
+    XmRange nvtx_range("xm_qy");
     Plan p;
     int rc = prepare(h, r, &p);
     if (rc) return rc;
@@ -721,6 +831,7 @@ static void print_log(const DevStats& S, const LogRec* L) {
 static int tr_common(xm_handle* h, int r, const double* R0, const double* s0, double lam, double* gradtol_inout,
                      double ls_step, const double* v, double max_time, double* R_out, double* s_out,
                      double* primal_out, xm_stats* stats, xm_log_rec* log, bool dev_ptrs) {
+    XmRange nvtx_range("xm_trust_region");
     Plan p;
     int rc = prepare(h, r, &p);
     if (rc) return rc;
@@ -793,6 +904,7 @@ extern "C" int xm_trust_region_dev(xm_handle* h, int r, const double* R0, const 
 // ------------------------------------------------------------------------------------------------ op-level hooks
 static int op_common(xm_handle* h, int r, int opcode, const double* R, const double* s, double lam, const double* P,
                      const double* ps, double lr, double* outR, double* outS, double* out_scalar) {
+    XmRange nvtx_range("xm_op");
     Plan p;
     int rc = prepare(h, r, &p);
     if (rc) return rc;

@@ -240,6 +240,7 @@ inline unsigned nblk(long long n, int t = 256) { return (unsigned)((n + t - 1) /
 // S X for a block of k >= 1 columns (device, ld = n3): slices of 3..20 columns through the product kernel + the block diagonal
 int apply_S(xm_handle* h, const double* L, const double* X, double* Y, int k, double* pad3_in, double* pad3_out, int* products) {
     const int n3 = h->n3, N = h->N;
+    const int wmax = (h->world > 1) ? std::max(3, std::min(h->comm_maxr, XM_MAX_RANK)) : XM_MAX_RANK;    // a communicator was sized for comm_maxr columns
     if (k < 3) {            // the kernel's minimum width: pad with zero columns
         CERT_CUDA(cudaMemsetAsync(pad3_in, 0, (size_t)n3 * 3 * sizeof(double), h->stream));
         CERT_CUDA(cudaMemcpyAsync(pad3_in, X, (size_t)n3 * k * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -250,7 +251,7 @@ int apply_S(xm_handle* h, const double* L, const double* X, double* Y, int k, do
     } else {
         int j0 = 0;
         while (j0 < k) {
-            int take = std::min(XM_MAX_RANK, k - j0);
+            int take = std::min(wmax, k - j0);
             const int rem = k - j0 - take;
             if (rem > 0 && rem < 3) take -= (3 - rem);
             int rc = xm_qy_dev(h, take, 1.0, X + (size_t)j0 * n3, Y + (size_t)j0 * n3);
@@ -275,10 +276,7 @@ int small_eigh(xm_handle* h, cusolverDnHandle_t cs, double* A, int m, int ld, do
     return XM_OK;
 }
 
-struct Blas {
-    cublasHandle_t cb = nullptr; cusolverDnHandle_t cs = nullptr;
-    ~Blas() { if (cb) cublasDestroy(cb); if (cs) cusolverDnDestroy(cs); }
-};
+struct Blas { cublasHandle_t cb = nullptr; cusolverDnHandle_t cs = nullptr; };     // views of the handle's cached library handles
 
 // ------------------------------------------------------------------------------------------------ block Davidson
 // lowest eigenpairs of S = Q + blockdiag(L).  sR (n3 x r): the near-null vectors that seed the block.  v_out_dev: n3.
@@ -403,9 +401,11 @@ int davidson_min_eig(xm_handle* h, Blas& bl, const double* L, const double* Dinv
 }  // namespace
 
 extern "C" int xm_op_diag_blocks_dev(xm_handle* h, double* out9N_dev);      // xm_capi.cu
+int xm_internal_libs(xm_handle* h, void** cublas_out, void** cusolver_out);    // xm_capi.cu: the handle's cached cuBLAS / cuSOLVER handles
 
 extern "C" int xm_certify_ex(xm_handle* h, int r, const double* R, const double* s, double lam, double primal, int method,
                              double* v_out, xm_cert_info* out) {
+    XmRange nvtx_range("xm_certify");
     if (!h || !R || !s) return XM_EINVAL;
     if (r < 3 || r > XM_MAX_RANK) return XM_EINVAL;
     if (h->N <= 0 || (!h->is_bsr && !h->Qp)) { h->err = "no Q set"; return XM_EINVAL; }
@@ -440,8 +440,8 @@ extern "C" int xm_certify_ex(xm_handle* h, int r, const double* R, const double*
     double w0 = 0, resid = 0;
     int products = 1, converged = 1;
     Blas bl;
-    if (cusolverDnCreate(&bl.cs) != CUSOLVER_STATUS_SUCCESS) { h->err = "cusolverDnCreate"; return XM_ECUDA; }
-    cusolverDnSetStream(bl.cs, h->stream);
+    int lrc = xm_internal_libs(h, (void**)&bl.cb, (void**)&bl.cs);
+    if (lrc) return lrc;
     if (method == XM_CERT_DENSE) {
         // dual slack on the device + full symmetric eigendecomposition, like checkeig.h:303-318
         double* S = mem.get<double>(col * n3); double* W = mem.get<double>(n3); int* info = mem.get<int>(1);
@@ -461,8 +461,6 @@ extern "C" int xm_certify_ex(xm_handle* h, int r, const double* R, const double*
         CERT_CUDA(cudaStreamSynchronize(h->stream));
         if (hinfo != 0) { h->err = "syevd did not converge"; return XM_ECUDA; }
     } else {
-        if (cublasCreate(&bl.cb) != CUBLAS_STATUS_SUCCESS) { h->err = "cublasCreate"; return XM_ECUDA; }
-        cublasSetStream(bl.cb, h->stream);
         double* Qd = mem.get<double>((size_t)N * 9); double* Dinv = mem.get<double>((size_t)N * 9);
         if (!Qd || !Dinv) { h->err = "certificate cudaMalloc failed"; return XM_ENOMEM; }
         rc = xm_op_diag_blocks_dev(h, Qd);                        // 3x3 diagonal blocks of Q (collective on a communicator)

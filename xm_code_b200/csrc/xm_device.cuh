@@ -23,7 +23,8 @@ constexpr int kLogCap = 1002;
 constexpr int kPartialBufs = 4;
 constexpr int kKC = 192;            // TMA ring: columns per chunk (box inner dimension, <= 256); see profiles/r01_sweep_ring_*.txt
 constexpr int kPartialStride = 1;   // doubles per slot; GT slots for the CTA sums + 1 for global CTA 0's flag, x kPartialBufs rotating buffers
-constexpr int kBsrChunk = 32;       // block-CSR: blocks per staged chunk (32 x 128 B = one 4 KB bulk copy; one column index per lane)
+constexpr int kBsrChunkMax = 32;    // block-CSR: blocks per staged chunk <= 32 (one column index per lane); Dev::bsr_chunk = 32 (512-thread CTAs:
+                                    // one 4 KB bulk copy per chunk) or 16 (1024-thread CTAs: 32 warps x 2 buffers x 2 KB fit shared memory)
 constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node that can share a solve (camera partition, peer-mapped exchange)
 
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
@@ -66,6 +67,12 @@ struct Dev {
     int push_plain;                            // operand exchange protocol: 0 = tagged words polled by the consumers (latency-bound
                                                // sizes: no fence, twice the bytes), 1 = plain stores into the peers' Xt published by a
                                                // .sys-fenced cross-GPU barrier (bandwidth-bound sizes: +3.5 us fence, half the bytes)
+    // boundary-only operand exchange (block-CSR on a communicator): a camera's rows go only to the ranks whose block rows reference
+    // it, and a rank unpacks only the remote cameras it references — on a view graph with locality (banded after an RCM ordering)
+    // that is a few percent of the rows; nullptr = every row to every rank (dense Q: every rank needs everything)
+    const unsigned char* peer_mask;            // bit w of peer_mask[i]: rank w's block rows reference camera i
+    const int* need_cams; int n_need;          // the remote cameras THIS rank's block rows reference, ascending
+    unsigned long long watchdog_ns;            // a barrier / tag wait longer than this raises the abort flag (XM_ESYNC)
     int* abort_peer[kMaxWorld];
     double* outR_peer[kMaxWorld];              // results in the wire layout (3N x r col-major / length N): every CTA stores its
     double* outS_peer[kMaxWorld];              // own cameras into every rank's copy
@@ -90,7 +97,8 @@ struct Dev {
                                // E <- beta E - 2 Q X(r_new); the product's operand is built from the new residual in the update
                                // phase and rides on the <r,r> reduction barrier (oracle study: tests/test_oracle.py)
     double *Xt;                // operand, r*ldq doubles (rows k >= n3 stay zero)  [== Xt_peer[rank]]
-    int bsr_stage, bsr_k8;     // block-CSR staging: 0 = one bulk-TMA copy per chunk, 1 = cp.async; gathers in flight per sub-warp: 4 or 8
+    int bsr_stage, bsr_k;      // block-CSR staging: 0 = one bulk-TMA copy per chunk, 1 = cp.async; gathers in flight per sub-warp: 2, 4 or 8
+    int bsr_chunk;             // blocks per staged chunk: 32 or 16 (see kBsrChunkMax)
     int x_cam_major;           // operand layout: 0 = j-major Xt[j*ldq + row] (dense paths, TMA boxes), 1 = camera-major Xt[row*r + j]
                                // (block-CSR: the 3r doubles a block needs are contiguous)
     double *partials;          // kPartialBufs * (G + 1) * kPartialStride: the reduction slots of THIS GPU's CTAs
@@ -315,7 +323,7 @@ struct Ctx {
         if ((++spins & 0x3ffu) != 0) return true;
         if (*(volatile int*)d.abort_flag) return false;
         // multi-GPU: generous — the ranks' hosts launch independently (a peer may reach its launch seconds later)
-        if (gtimer() - t0 > (world() > 1 ? 30000000000ull : 4000000000ull)) { raise_abort(); return false; }
+        if (gtimer() - t0 > d.watchdog_ns) { raise_abort(); return false; }
         return true;
     }
     // warp 0: fixed-order sum of the first `n` slots; the flag sits in slot n.  Every lane returns the totals.
@@ -496,14 +504,16 @@ struct Ctx {
     __device__ __forceinline__ void unpack_operand() {
         if (world() == 1 || d.push_plain) return;
         const unsigned long long t0 = gtimer();
-        const int nrem = d.n3 - d.nown;
+        const int nrem = d.need_cams ? 3 * d.n_need : d.n3 - d.nown;      // remote rows this rank consumes
         const long long total = (long long)d.r * nrem;
         int bad = 0;
         for (long long e = (long long)blockIdx.x * NT + tid; e < total; e += (long long)d.G * NT) {
             int jj, idx;                                      // consecutive threads walk the layout's fast axis
             if (d.x_cam_major) { idx = (int)(e / d.r); jj = (int)(e - (long long)idx * d.r); }
             else               { jj = (int)(e / nrem); idx = (int)(e - (long long)jj * nrem); }
-            const int row = idx < d.row0 ? idx : idx + d.nown;
+            int row;
+            if (d.need_cams) row = 3 * d.need_cams[idx / 3] + idx % 3;     // boundary-only: the idx-th needed remote row
+            else             row = idx < d.row0 ? idx : idx + d.nown;
             const size_t off = d.x_cam_major ? (size_t)row * d.r + jj : (size_t)jj * d.ldq + row;
             double v;
             unsigned spins = 0;
@@ -551,9 +561,10 @@ __device__ __forceinline__ void st_operand(const C& c, int i, bool act, const do
         double* p = c.d.Xt + off;
         p[0] = x[0]; p[rs] = x[1]; p[2 * rs] = x[2];
         if (c.world() > 1) {
+            const unsigned mask = c.d.peer_mask ? c.d.peer_mask[i] : 0xffu;     // boundary-only: the ranks that reference camera i
 #pragma unroll 1
             for (int w = 0; w < c.world(); ++w) {
-                if (w == c.d.rank) continue;
+                if (w == c.d.rank || !((mask >> w) & 1u)) continue;
                 if (c.d.push_plain) {
                     double* q = c.d.Xt_peer[w] + off;
                     q[0] = x[0]; q[rs] = x[1]; q[2 * rs] = x[2];
@@ -637,7 +648,7 @@ __device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, 
 // Block-CSR Q.Y: one warp per block row (camera), blocks stored 4x4 row-major = one 128-byte line each (row / column 3 are
 // zero padding for bdim == 3), operand CAMERA-MAJOR (Xt[(3c+a) r + j]: the 3r doubles a block needs are adjacent).
 //
-//   * Q blocks: the warp stages its row through shared memory in chunks of kBsrChunk = 32 blocks — ONE 4 KB bulk copy (1-D TMA,
+//   * Q blocks: the warp stages its row through shared memory in chunks of Dev::bsr_chunk = 32 (or 16) blocks — ONE 4 KB (2 KB) bulk copy (1-D TMA,
 //     cp.async.bulk, L2 evict_first) per chunk into one of the warp's two buffers, completion on the warp's own mbarrier;
 //     the next chunk (of this row, or the first of the warp's next row) is in flight while the current one is consumed, so
 //     ~64 KB of Q per SM are in flight without holding a register.  (bsr_stage = 1 stages with eight warp-wide 16-byte
@@ -655,15 +666,15 @@ __device__ __forceinline__ void qy_sweep_dense(const Dev& d, int cam, int kbeg, 
 // of its own 128 B (no locality to exploit: each camera's row is read by ~100 random rows), and Q + gathers together move
 // at ~5.5 TB/s for r = 5, 10 and 20 alike; eight gathers in flight instead of four is slower.
 struct BsrCursor {           // the warp's position in its sequence of chunks: rows cam, cam + CB, ... ; chunks part, part + nparts, ...
-    int cam, q, rb0, rb1;
+    int cam, q, rb0, rb1, ch;   // ch = blocks per chunk (Dev::bsr_chunk)
     __device__ __forceinline__ bool valid() const { return cam >= 0; }
-    __device__ __forceinline__ int start() const { return rb0 + q * kBsrChunk; }
-    __device__ __forceinline__ int count() const { return min(kBsrChunk, rb1 - start()); }
+    __device__ __forceinline__ int start() const { return rb0 + q * ch; }
+    __device__ __forceinline__ int count() const { return min(ch, rb1 - start()); }
 };
 __device__ __forceinline__ void bsr_seek(const Dev& d, BsrCursor& cu, int cam_hi, int part, int CB) {   // first non-empty chunk at or after (cam, q)
     while (cu.cam < cam_hi) {
         cu.rb0 = d.bsr_rowptr[cu.cam - d.cam0]; cu.rb1 = d.bsr_rowptr[cu.cam - d.cam0 + 1];
-        if (cu.rb0 + cu.q * kBsrChunk < cu.rb1) return;
+        if (cu.rb0 + cu.q * cu.ch < cu.rb1) return;
         cu.cam += CB; cu.q = part;
     }
     cu.cam = -1;
@@ -676,15 +687,15 @@ __device__ __forceinline__ int bsr_issue(C& c, const BsrCursor& cu, int buf, uns
     if (d.bsr_stage == 0) {                                  // one bulk-TMA copy per chunk
         if (c.lane == 0) {
             mbar_expect_tx(&c.bsr_bar[buf], (unsigned)nb * 128u);
-            tma_load_1d_stream(c.bsr_buf + (size_t)buf * kBsrChunk * 16, d.bsr_val + (size_t)st * 16, (unsigned)nb * 128u, &c.bsr_bar[buf], policy);
+            tma_load_1d_stream(c.bsr_buf + (size_t)buf * cu.ch * 16, d.bsr_val + (size_t)st * 16, (unsigned)nb * 128u, &c.bsr_bar[buf], policy);
         }
         return (c.lane < nb) ? __ldg(d.bsr_col + st + c.lane) : 0;
     }
-    const unsigned dst = smem_u32(c.bsr_buf + (size_t)buf * kBsrChunk * 16) + (unsigned)c.lane * 16u;
+    const unsigned dst = smem_u32(c.bsr_buf + (size_t)buf * cu.ch * 16) + (unsigned)c.lane * 16u;
     const char* src = reinterpret_cast<const char*>(d.bsr_val + (size_t)st * 16) + c.lane * 16;
     const int nbytes = nb * 128;
 #pragma unroll
-    for (int k = 0; k < kBsrChunk * 128 / 512; ++k)
+    for (int k = 0; k < kBsrChunkMax * 128 / 512; ++k)
         if (k * 512 + c.lane * 16 < nbytes) cp_async16_stream(dst + k * 512, src + k * 512, policy);
     cp_async_commit();
     return (c.lane < nb) ? __ldg(d.bsr_col + st + c.lane) : 0;
@@ -702,7 +713,7 @@ __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, b
         if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();                                        // the lanes' copies are visible to the whole warp
     }
-    const unsigned sbuf = smem_u32(c.bsr_buf + (size_t)buf * kBsrChunk * 16);
+    const unsigned sbuf = smem_u32(c.bsr_buf + (size_t)buf * d.bsr_chunk * 16);
     const double* xc = d.Xt;
     for (int g0 = 0; g0 < nb; g0 += K * cpw) {               // warp-uniform trip count
         double x[K][3];
@@ -858,7 +869,7 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
     const int kend = (int)(((long long)(ks + 1) * steps) / KS) * 64;
     // block-CSR: the warp's chunk pipeline runs across the batches (the next row's first chunk is already in flight while the
     // CTA finishes the current batch's epilogue)
-    BsrCursor cur{-1, 0, 0, 0};
+    BsrCursor cur{-1, 0, 0, 0, d.bsr_chunk};
     int col_cur = 0, buf_cur = 0;
     unsigned long long policy = 0;
     if (BSR) {
@@ -877,8 +888,9 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
                 bsr_seek(d, nxt, c.cam_hi, ks, CB);
                 int col_nxt = 0;
                 if (nxt.valid()) col_nxt = bsr_issue(c, nxt, buf_cur ^ 1, policy);
-                if (d.bsr_k8) bsr_consume<8>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);       // deeper gather
-                else          bsr_consume<4>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+                if (d.bsr_k == 2)      bsr_consume<2>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);     // gathers in flight per sub-warp
+                else if (d.bsr_k == 8) bsr_consume<8>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+                else                   bsr_consume<4>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
                 cur = nxt; col_cur = col_nxt; buf_cur ^= 1;
             }
             for (int off = c.W; off < 32; off <<= 1) {      // fixed-order butterfly over the warp's sub-warps
@@ -1075,8 +1087,8 @@ __device__ __forceinline__ void ring_init(Ctx<RP, NT, MG>& c, unsigned char* dyn
     if (d.bsr_val) {          // block-CSR: two staged chunks + two mbarriers per warp
         constexpr int NWARPS = NT / 32;
         double* bufs = reinterpret_cast<double*>(base);
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufs + (size_t)NWARPS * 2 * kBsrChunk * 16);
-        c.bsr_buf = bufs + (size_t)c.warp * 2 * kBsrChunk * 16;
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufs + (size_t)NWARPS * 2 * d.bsr_chunk * 16);
+        c.bsr_buf = bufs + (size_t)c.warp * 2 * d.bsr_chunk * 16;
         c.bsr_bar = bars + c.warp * 2;
         if (c.lane == 0) { mbar_init(&c.bsr_bar[0], 1); mbar_init(&c.bsr_bar[1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

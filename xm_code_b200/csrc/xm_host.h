@@ -15,6 +15,8 @@ struct xm_handle {
     double* Qp = nullptr; size_t Qp_cap = 0;          // padded row-major dense Q
     double* Qstage = nullptr; size_t Qstage_cap = 0;   // staging for the user's column-major matrix
     int* bsr_rowptr = nullptr; int* bsr_col = nullptr; double* bsr_val = nullptr; int bsr_bdim = 0; bool is_bsr = false;
+    // boundary-only operand exchange of a block-CSR operator on a communicator (xm_set_q_bsr): see Dev::peer_mask / need_cams
+    unsigned char* d_peer_mask = nullptr; int* d_need_cams = nullptr; int n_need = 0; long long halo_sent = 0;
     // workspace (one allocation, carved per (N, r))
     char* ws = nullptr; size_t ws_cap = 0; int ws_r = -1, ws_N = -1, ws_G = -1, ws_ldq = -1, ws_bsr = -1;
     xm::Dev dev{};                                         // pointer template, filled by carve()
@@ -28,6 +30,9 @@ struct xm_handle {
     // pinned host mirrors
     xm::DevStats* h_stats = nullptr; xm::LogRec* h_log = nullptr;
     int launches = 0;
+    // cuBLAS / cuSOLVER handles of the certificate and the assembly (plain library GEMM / Cholesky / small eigen-solves), created on
+    // first use and kept: creating and destroying them per call costs tens of milliseconds and device-wide synchronisations
+    void* cublas = nullptr; void* cusolver = nullptr;
     // TMA descriptors (2-D tensor maps) for the dense Q and the current operand buffer
     CUtensorMap mapQ[3]{}, mapX{};
     void* encode_tiled = nullptr;       // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -42,6 +47,13 @@ struct xm_handle {
     char* peer_arena[xm::kMaxWorld] = {};
     bool peer_ipc[xm::kMaxWorld] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
     size_t off_bar = 0, off_abort = 0, off_partials = 0, off_ll = 0, off_slots = 0, off_xt = 0, off_xtll = 0, off_outR = 0, off_outS = 0;
+};
+
+// NVTX range around a C-ABI call (header-only NVTX v3: a no-op unless a profiler is attached)
+#include <nvtx3/nvToolsExt.h>
+struct XmRange {
+    explicit XmRange(const char* name) { nvtxRangePushA(name); }
+    ~XmRange() { nvtxRangePop(); }
 };
 
 #define XM_CUDA(h, call)                                                                           \

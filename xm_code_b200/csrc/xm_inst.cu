@@ -28,50 +28,42 @@ static cudaError_t launch_t(int kind, const xm_handle* h, const Dev& d, int opco
     return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(NT), args, dyn, st);
 }
 
-// block-CSR kernels hold 3 accumulators per lane whatever the rank: 512 threads for every RP
-template <int RP>
-static cudaError_t launch_bsr(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
-    const void* fn = (kind == 0) ? (const void*)xm_solve_kernel<RP, 512, kPath, kMG> : (const void*)xm_ops_kernel<RP, 512, kPath, kMG>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    if (kind == 0) {
-        void* args[] = {(void*)&d, (void*)h->mapQ, (void*)&h->mapX};
-        return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(512), args, dyn, st);
-    }
-    void* args[] = {(void*)&d, (void*)h->mapQ, (void*)&h->mapX, (void*)&opcode};
-    return cudaLaunchCooperativeKernel(fn, dim3(d.G), dim3(512), args, dyn, st);
+// block-CSR kernels hold 3 accumulators per lane whatever the rank: the same thread count for every RP — 1024 (the default: resident
+// warps hide the operand gather's latency) or 512 (A/B hook XM_TUNE_BSR_NT); the plan decides (d.NW)
+template <int RP, int NT_DENSE>
+static cudaError_t launch_rp(int kind, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
+#if XM_INST_PATH == 2
+    if (d.NW == 32) return launch_t<RP, 1024>(kind, h, d, opcode, dyn, st);
+    return launch_t<RP, 512>(kind, h, d, opcode, dyn, st);
+#else
+    return launch_t<RP, NT_DENSE>(kind, h, d, opcode, dyn, st);
+#endif
 }
 
 #if XM_INST_GROUP == 0
 cudaError_t XM_GROUP_FN(0, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
-        case 3: return launch_t<3, 512>(kind, h, d, opcode, dyn, st);
-        case 4: return launch_t<4, 512>(kind, h, d, opcode, dyn, st);
-        case 5: return launch_t<5, 512>(kind, h, d, opcode, dyn, st);
+        case 3: return launch_rp<3, 512>(kind, h, d, opcode, dyn, st);
+        case 4: return launch_rp<4, 512>(kind, h, d, opcode, dyn, st);
+        case 5: return launch_rp<5, 512>(kind, h, d, opcode, dyn, st);
     }
     return cudaErrorInvalidValue;
 }
 #elif XM_INST_GROUP == 1
 cudaError_t XM_GROUP_FN(1, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
-        case 6: return launch_t<6, 512>(kind, h, d, opcode, dyn, st);
-        case 8: return launch_t<8, 512>(kind, h, d, opcode, dyn, st);
-        case 10: return launch_t<10, 512>(kind, h, d, opcode, dyn, st);
+        case 6: return launch_rp<6, 512>(kind, h, d, opcode, dyn, st);
+        case 8: return launch_rp<8, 512>(kind, h, d, opcode, dyn, st);
+        case 10: return launch_rp<10, 512>(kind, h, d, opcode, dyn, st);
     }
     return cudaErrorInvalidValue;
 }
 #else
 cudaError_t XM_GROUP_FN(2, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
-#if XM_INST_PATH == 2
-        case 12: return launch_bsr<12>(kind, h, d, opcode, dyn, st);
-        case 16: return launch_bsr<16>(kind, h, d, opcode, dyn, st);
-        case 20: return launch_bsr<20>(kind, h, d, opcode, dyn, st);
-#else
-        case 12: return launch_t<12, 256>(kind, h, d, opcode, dyn, st);
-        case 16: return launch_t<16, 256>(kind, h, d, opcode, dyn, st);
-        case 20: return launch_t<20, 256>(kind, h, d, opcode, dyn, st);
-#endif
+        case 12: return launch_rp<12, 256>(kind, h, d, opcode, dyn, st);
+        case 16: return launch_rp<16, 256>(kind, h, d, opcode, dyn, st);
+        case 20: return launch_rp<20, 256>(kind, h, d, opcode, dyn, st);
     }
     return cudaErrorInvalidValue;
 }

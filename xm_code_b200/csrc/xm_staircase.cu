@@ -17,6 +17,7 @@ static void banner(bool on, const char* text) {
 
 extern "C" int xm_solve(xm_handle* h, int mode, int max_rank, double tol, double lam, double max_time, const double* s_init,
                         int cert_method, double* R_out, double* s_out, xm_solve_result* res) {
+    XmRange nvtx_range("xm_solve");
     if (!h || !R_out || !s_out) return XM_EINVAL;
     if (mode != XM_MODE_FULL && mode != XM_MODE_RANK3 && mode != XM_MODE_REBUTTLE) return XM_EINVAL;
     if (h->N <= 0) { h->err = "no Q set"; return XM_EINVAL; }

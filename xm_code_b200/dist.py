@@ -87,12 +87,7 @@ def rcm_camera_order(rowptr, colidx):
     """Reverse Cuthill-McKee order of the cameras of a block-CSR view graph ("simple BFS/RCM bands"): cameras
     that see each other end up close together, so the library's contiguous camera ranges become a band partition with few
     boundary cameras.  Returns perm with perm[new] = old."""
-    import scipy.sparse as sp
-    from scipy.sparse.csgraph import reverse_cuthill_mckee
-    rowptr = np.asarray(rowptr); colidx = np.asarray(colidx)
-    n = rowptr.size - 1
-    g = sp.csr_matrix((np.ones(colidx.size, dtype=np.int8), colidx, rowptr), shape=(n, n))
-    return np.asarray(reverse_cuthill_mckee(g, symmetric_mode=True), dtype=np.int64)
+    return capi.rcm_order(rowptr, colidx)          # xm_rcm_order (host C++ in the library)
 
 
 def permute_bsr(rowptr, colidx, vals, perm):

@@ -148,7 +148,22 @@ def erdos_renyi_bsr(n_cameras: int, avg_degree: float = 100.0, seed: int = 0, sh
     ii, jj = ii[ok], jj[ok]
     path_i = np.arange(N - 1); path_j = np.arange(1, N)
     ei = np.concatenate([path_i, np.minimum(ii, jj)]); ej = np.concatenate([path_j, np.maximum(ii, jj)])
-    key = np.unique(ei.astype(np.int64) * N + ej)
+    return _bsr_from_edges(N, ei, ej, rng, shared)
+
+
+def banded_bsr(n_cameras: int, half_bandwidth: int = 6, seed: int = 0, shared: int = 4):
+    """Block-sparse PSD operator on a BANDED view graph (camera i sees cameras i+1 .. i+half_bandwidth: a video-like capture) —
+    the case where a graph-cut camera partition pays: contiguous camera ranges only share a thin boundary.  Same edge model and
+    return convention as ``erdos_renyi_bsr``."""
+    rng = np.random.default_rng(seed)
+    N = int(n_cameras)
+    ei = np.concatenate([np.arange(N - k) for k in range(1, half_bandwidth + 1)])
+    ej = np.concatenate([np.arange(k, N) for k in range(1, half_bandwidth + 1)])
+    return _bsr_from_edges(N, ei, ej, rng, shared)
+
+
+def _bsr_from_edges(N, ei, ej, rng, shared):
+    key = np.unique(np.minimum(ei, ej).astype(np.int64) * N + np.maximum(ei, ej))
     ei = (key // N).astype(np.int64); ej = (key % N).astype(np.int64)
     E = ei.size
     Rg = random_rotations(N, rng)
