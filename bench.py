@@ -223,6 +223,47 @@ def latency_regime(torch, capi, stream, peak, steps=3):
     return out
 
 
+def bsr_er100k(torch, capi, xdist, world, rank, local, stream, peak):
+    """BASELINE config 5: synthetic Erdos-Renyi view graph, 100k cameras / ~5M edges, block-CSR Q (one 128-byte block per directed edge),
+    r in {5, 10, 20}: the block-CSR Q.Y alone and a short time-capped solve, on this run's GPUs (cameras partitioned when world > 1).
+    Algorithmic bytes per GPU: nnzb (128 + 4) + 4 (N + 1) + 8 * 3N r (operand) + 8 * 3 rows r (result)."""
+    import torch.distributed as dist
+    from xm_code_b200 import problems
+    N = int(os.environ.get("XM_BENCH_BSR_CAMERAS", "100000"))
+    rowptr, col, vals = problems.erdos_renyi_bsr(N, avg_degree=100.0, seed=0)
+    h = capi.Handle(device=local)
+    lo, hi = 0, N
+    if world > 1:
+        info = xdist.attach(h, N, 20)
+        lo, hi = info["cam_lo"], info["cam_hi"]
+    h.set_stream(stream.cuda_stream)
+    h.set_q_bsr(rowptr, col, vals, 3)
+    nnzb_local = int(rowptr[hi] - rowptr[lo])
+    out = {"workload": f"Erdos-Renyi view graph + Hamiltonian path, {N} cameras, {int(rowptr[-1])} directed 3x3 blocks (128 B padded each), block-CSR",
+           "nnzb": int(rowptr[-1]), "halo": h.comm_halo() if world > 1 else None, "ranks": {}}
+    rng = np.random.default_rng(1)
+    for r in (5, 10, 20):
+        X = torch.from_numpy(rng.standard_normal((r, 3 * N))).cuda(); O = torch.empty_like(X)
+        h.qy_dev(r, X.data_ptr(), O.data_ptr())
+        v = [h.bench_qy(r, 20), h.bench_qy(r, -20)]
+        R0 = identity_start(torch, N, r, "cuda"); s0 = torch.ones(N, dtype=torch.float64, device="cuda")
+        Rd = torch.empty_like(R0); sd = torch.empty_like(s0)
+        primal, _, st = h.trust_region_dev(r, R0.data_ptr(), s0.data_ptr(), Rd.data_ptr(), sd.data_ptr(), lam=0.0, gradtol=1e-6, max_time=1.0)
+        v += [st["solve_ms"], float(st["tcg_iters"]), float(st["qy_products"])]
+        if world > 1:
+            t = torch.tensor(v[:3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); v[:3] = [float(x) for x in t.tolist()]
+        alg = nnzb_local * (128 + 4) + 4 * (hi - lo + 1) + 8 * 3 * N * r + 8 * 3 * (hi - lo) * r
+        out["ranks"][f"r{r}"] = {"ms_per_product_free_running": v[0], "ms_per_product_lockstep": v[1], "algorithmic_bytes_per_gpu": alg,
+                                 "frac_of_hbm_peak_lockstep": alg / (v[1] * 1e-3) / 1e9 / peak,
+                                 "solve_tcg_iters_per_s": v[3] / (v[2] * 1e-3), "solve_ms_per_product": v[2] / max(1.0, v[4])}
+    if world > 1:
+        xdist.detach(h)
+    else:
+        h.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -350,7 +391,7 @@ def run_ours(args):
     alg = lambda r: 8.0 * rows_max * n3 + 8.0 * n3 * r + 8.0 * rows_max * r      # noqa: E731
     peak, peak_src = measured_peak_gbs()
     extras = {}
-    if world == 1 and rank == 0:
+    if world == 1 and rank == 0 and int(os.environ.get("XM_BENCH_EXTRAS", "1")):
         # certificate (f1) on the full-solve point and assembly (f2) of this very problem through the C-ABI
         try:
             if full:
@@ -371,6 +412,14 @@ def run_ours(args):
         extras["latency_regime"] = latency_regime(torch, capi, stream, peak)
     if world > 1:
         xdist.detach(h)
+    else:
+        h.close()
+    if int(os.environ.get("XM_BENCH_BSR", "1")) and int(os.environ.get("XM_BENCH_EXTRAS", "1")):
+        torch.cuda.empty_cache()
+        try:
+            extras["bsr_er100k"] = bsr_er100k(torch, capi, xdist, world, rank, local, stream, peak)
+        except Exception as e:  # noqa: BLE001
+            extras["bsr_er100k"] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         return
     # ONE solve shared by all ranks: the job's iterations are the solve's iterations (strong scaling for world > 1)

@@ -14,13 +14,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
-# GPU tests written after the round's GPU budget ran out (they have passed only with the oracle standing in for the device
-# calls): run them LAST, so that under `-x` a surprise there cannot mask the suite that HAS been validated on a B200.
-_NOT_YET_RUN_ON_A_GPU = ("test_certificate_solver.py", "test_gpu_errors.py", "test_xm2.py")
+# The loop-back multi-GPU tests (two cooperative kernels co-resident on one GPU) and the tests that page in cuSOLVER / cuBLAS run
+# LAST: under `-x` a surprise there cannot mask the single-GPU parity suite.
+_RUN_LATE = ("test_gpu_multi.py", "test_reference_scripts.py")
 
 
 def pytest_collection_modifyitems(config, items):
-    late = [it for it in items if it.get_closest_marker("gpu") and os.path.basename(str(it.fspath)) in _NOT_YET_RUN_ON_A_GPU]
+    late = [it for it in items if it.get_closest_marker("gpu") and os.path.basename(str(it.fspath)) in _RUN_LATE]
     if late:
         ids = {id(it) for it in late}
         items[:] = [it for it in items if id(it) not in ids] + late

@@ -36,6 +36,8 @@ def test_c3_bal1723_matches_reference_output_and_c_oracle(gpu_handle_factory):
     N = 1723
     Q, _ = problems.synthetic_dense_q(N, seed=0, obs_per_camera=60, n_landmarks=12 * N)
     rows, total, js = parse_reference_log(os.path.join(GOLD, "ref_bal1723", "log.txt"))
+    restart = [n for n, row in enumerate(rows) if row[0] == 0]           # the golden log holds three identical repeats of the solve
+    rows = rows[:restart[1]] if len(restart) > 1 else rows
     s_ref = load_bin(os.path.join(GOLD, "ref_bal1723", "s_ref.bin"))[:, 0]
     primal_ref = js["runs"][-1]["primal"]
     # the reference's order of operations inside a tCG iteration (three barriers): iteration counts within 5 % of the reference run;

@@ -180,6 +180,97 @@ __global__ void __launch_bounds__(NT, 1) k_stage(const P p) {
     }
 }
 
+// ---- stage4: k_stage with the operand laid out [camera][column][4] (3 rows + pad = 32 bytes): ONE 256-bit gather per lane and block
+template <int NT, int K, int CH>
+__global__ void __launch_bounds__(NT, 1) k_stage4(const P p, const double* __restrict__ X4) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = p.W, cpw = p.cpw, sw = lane / W, j = lane % W, r = p.r;
+    const bool act = j < r;
+    double* buf = reinterpret_cast<double*>(smem) + (size_t)warp * 2 * CH * 16;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(smem) + (size_t)NW * 2 * CH * 16) + warp * 2;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const int nwarps = gridDim.x * NW;
+    int row = blockIdx.x * NW + warp;
+    int b0 = 0, b1 = 0, q = 0;
+    auto seek = [&]() {
+        while (row < p.N) {
+            b0 = p.rowptr[row]; b1 = p.rowptr[row + 1];
+            if (b0 + q * CH < b1) return true;
+            row += nwarps; q = 0;
+        }
+        return false;
+    };
+    auto issue = [&](int rb0, int rb1, int qq, int bf) {
+        const int st = rb0 + qq * CH, nb = min(CH, rb1 - st);
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[bf])), "r"((unsigned)nb * 128u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(smem_u32(buf + (size_t)bf * CH * 16)), "l"(p.val + (size_t)st * 16), "r"((unsigned)nb * 128u), "r"(smem_u32(&bar[bf])), "l"(policy) : "memory");
+        }
+        return (lane < nb) ? __ldg(p.col + st + lane) : 0;
+    };
+    unsigned phase = 0;
+    int bf = 0, colreg = 0;
+    bool have = seek();
+    if (have) colreg = issue(b0, b1, q, 0);
+    double e0 = 0, e1 = 0, e2 = 0;
+    while (have) {
+        const int crow = row, cb0 = b0, cb1 = b1, cq = q;
+        q += 1;
+        bool more = seek();
+        int colnext = 0;
+        if (more) colnext = issue(b0, b1, q, bf ^ 1);
+        {
+            unsigned ok = 0;
+            while (!ok) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(&bar[bf])), "r"((phase >> bf) & 1u) : "memory");
+            phase ^= 1u << bf;
+        }
+        const int st = cb0 + cq * CH, nb = min(CH, cb1 - st);
+        const unsigned sb = smem_u32(buf + (size_t)bf * CH * 16);
+        for (int g0 = 0; g0 < nb; g0 += K * cpw) {
+            double x[K][4];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int bi = g0 + k * cpw + sw;
+                const int c = __shfl_sync(0xffffffffu, colreg, bi & 31);
+                x[k][0] = x[k][1] = x[k][2] = x[k][3] = 0.0;
+                if (act && bi < nb) {
+                    const double* xp = X4 + ((size_t)c * r + j) * 4;
+                    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x[k][0]), "=d"(x[k][1]), "=d"(x[k][2]), "=d"(x[k][3]) : "l"(xp));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int bi = g0 + k * cpw + sw;
+                if (bi < nb) {
+                    const unsigned qa = sb + (unsigned)bi * 128u;
+                    const double2 a0 = lds_v2(qa), a1 = lds_v2(qa + 16), c0 = lds_v2(qa + 32), c1 = lds_v2(qa + 48), d0 = lds_v2(qa + 64), d1 = lds_v2(qa + 80);
+                    e0 = fma(a0.x, x[k][0], e0); e0 = fma(a0.y, x[k][1], e0); e0 = fma(a1.x, x[k][2], e0);
+                    e1 = fma(c0.x, x[k][0], e1); e1 = fma(c0.y, x[k][1], e1); e1 = fma(c1.x, x[k][2], e1);
+                    e2 = fma(d0.x, x[k][0], e2); e2 = fma(d0.y, x[k][1], e2); e2 = fma(d1.x, x[k][2], e2);
+                }
+            }
+        }
+        const bool row_done = !more || row != crow;
+        if (row_done) {
+            for (int off = W; off < 32; off <<= 1) { e0 += shfl_xor_d(e0, off); e1 += shfl_xor_d(e1, off); e2 += shfl_xor_d(e2, off); }
+            if (lane < W && act) { double* o = p.out + (size_t)(3 * crow) * r + j; o[0] = e0; o[r] = e1; o[2 * r] = e2; }
+            e0 = e1 = e2 = 0;
+        }
+        have = more; colreg = colnext; bf ^= 1;
+    }
+}
+
 template <typename F>
 static float time_ms(F launch, int iters) {
     cudaEvent_t a, b;
@@ -248,6 +339,17 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(k_stage<NT, K, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         report("stage  NT=" #NT " K=" #K " CH=" #CH " 1 CTA/SM", time_ms([&]() { k_stage<NT, K, CH><<<SM, NT, sm>>>(p); }, iters)); } while (0)
 #define RUN_DIRECT(NT, K) report("direct NT=" #NT " K=" #K " 1024/NT CTA/SM", time_ms([&]() { k_direct<NT, K><<<SM * (1024 / NT), NT>>>(p); }, iters))
+    // operand in the [camera][column][4] layout for the stage4 variants
+    std::vector<double> X4h((size_t)N * r * 4, 0.0);
+    for (int c = 0; c < N; ++c) for (int jj = 0; jj < r; ++jj) for (int a = 0; a < 3; ++a) X4h[((size_t)c * r + jj) * 4 + a] = X[(size_t)c * xs + (size_t)a * r + jj];
+    double* d_X4; CK(cudaMalloc(&d_X4, sizeof(double) * X4h.size())); CK(cudaMemcpy(d_X4, X4h.data(), sizeof(double) * X4h.size(), cudaMemcpyHostToDevice));
+#define RUN_STAGE4(NT, K, CH) do { \
+        const size_t sm = (size_t)(NT / 32) * 2 * (CH * 128 + 8); \
+        CK(cudaFuncSetAttribute(k_stage4<NT, K, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        report("stage4 NT=" #NT " K=" #K " CH=" #CH " v4 operand", time_ms([&]() { k_stage4<NT, K, CH><<<SM, NT, sm>>>(p, d_X4); }, iters)); } while (0)
+    RUN_STAGE4(1024, 2, 16);
+    RUN_STAGE4(1024, 4, 16);
+    RUN_STAGE4(512, 4, 32);
     RUN_STAGE(512, 4, 32);      // the library's configuration
     RUN_STAGE(512, 8, 32);
     RUN_STAGE(512, 4, 16);      // half-size chunks (isolates the chunk-size effect of the next two)

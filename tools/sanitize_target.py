@@ -99,9 +99,10 @@ if "multi" in WHAT:
         X = rng.standard_normal((3 * Nn, 4))
         for o in call("qy", X, 1.0):
             assert rel(o, Qm @ X) < 1e-12
-        ref = xo.trust_region(Qm, xo.identity_init(Nn, 4), np.ones(Nn), 0.0, 1e-7)
-        for g in call("trust_region", xo.from_blocks(xo.identity_init(Nn, 4)), np.ones(Nn), 0.0, 1e-7):
-            assert abs(g.primal - ref.primal) <= 1e-7 * abs(ref.primal)
+        tol = 1.0 if case == "bsr-halo" else 1e-7           # a chain-like graph needs thousands of iterations to 1e-7: stop early, same path
+        ref = xo.trust_region(Qm, xo.identity_init(Nn, 4), np.ones(Nn), 0.0, tol)
+        for g in call("trust_region", xo.from_blocks(xo.identity_init(Nn, 4)), np.ones(Nn), 0.0, tol):
+            assert abs(g.primal - ref.primal) <= 1e-7 * abs(ref.primal), (case, g.primal, ref.primal)
         print("multi", case, "ok", flush=True)
         for hh in hs:
             hh.comm_disconnect()

@@ -878,6 +878,40 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
         bsr_seek(d, cur, c.cam_hi, ks, CB);
         if (cur.valid()) col_cur = bsr_issue(c, cur, 0, policy);
     }
+    if (BSR && KS == 1) {
+        // One warp per block row and nothing shared between rows: every warp free-runs through its own rows (cam_lo + warp,
+        // + CB, ...) and finishes each row's per-camera epilogue itself, straight from the registers the butterfly leaves — no
+        // CTA-wide barrier per batch, so a long row does not hold up 31 other warps and the chunk pipeline never drains
+        // (measured on ER-100k: the per-batch barriers cost 20-45 % of the product at 1024 threads).  Sub-warp 0 of the warp runs
+        // the epilogue, the other sub-warps shadow it without storing (they hold the same totals).
+        for (int cam = c.cam_lo + cslot; cam < c.cam_hi; cam += CB) {          // warp-uniform
+            double E[3] = {0.0, 0.0, 0.0};
+            while (cur.valid() && cur.cam == cam) {
+                BsrCursor nxt = cur;
+                nxt.q += 1;
+                bsr_seek(d, nxt, c.cam_hi, 0, CB);
+                int col_nxt = 0;
+                if (nxt.valid()) col_nxt = bsr_issue(c, nxt, buf_cur ^ 1, policy);
+                if (d.bsr_k == 2)      bsr_consume<2>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+                else if (d.bsr_k == 8) bsr_consume<8>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+                else                   bsr_consume<4>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+                cur = nxt; col_cur = col_nxt; buf_cur ^= 1;
+            }
+            for (int off = c.W; off < 32; off <<= 1) {      // fixed-order butterfly over the warp's sub-warps: every lane gets its column's total
+                E[0] += shfl_xor_d(E[0], off); E[1] += shfl_xor_d(E[1], off); E[2] += shfl_xor_d(E[2], off);
+            }
+            const bool valid = (c.sw == 0);
+            if (MODE == MODE_OUT) {
+                const double o[3] = {d.qy_alpha * E[0], d.qy_alpha * E[1], d.qy_alpha * E[2]};
+                st_out3(c, cam, valid && c.act, o);
+            } else if (MODE == MODE_HESS) {
+                part += epi_hess<RP, NT, MG>(c, cam, E, valid);
+            } else {
+                part += epi_obj<RP, NT, MG>(c, cam, E, oa, valid);
+            }
+        }
+        return part;
+    }
     for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
         const int cam = b0 + cslot;
         if (BSR) {

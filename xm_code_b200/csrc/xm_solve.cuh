@@ -204,6 +204,7 @@ __device__ __forceinline__ void phase_dir(Ctx<RP, NT, MG>& c, double beta) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[a] = beta * p[a] - rr[a];
         st3(c.R(V_P), i, r, c.j, act, p);
+        __syncwarp();                                   // every lane of the sub-warp has read S_PS[i] before lane 0 rewrites it (racecheck)
         if (valid && c.j == 0 && i > 0) c.S(S_PS)[i] = psi;
         double x[3] = {si * p[0] + psi * y[0], si * p[1] + psi * y[1], si * p[2] + psi * y[2]};
         st_operand(c, i, act, x);
