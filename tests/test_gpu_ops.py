@@ -55,6 +55,21 @@ def test_qy_launch_geometries(gpu_handle_factory, grid, ks, variant):
     assert rel(h.qy(2 * X), 2 * Q @ X) < TOL          # second call on the same handle (ring state is per launch)
 
 
+@pytest.mark.parametrize("r", [8, 10])
+@pytest.mark.parametrize("grid,ks", [(1, 1), (1, 7), (3, 0), (16, 0), (148, 0), (40, 7), (97, 0)])
+def test_qy_two_cameras_per_warp_geometries(gpu_handle_factory, grid, ks, r):
+    """Padded ranks 8 / 10 run 256-thread CTAs whose consumer warps sweep TWO cameras per operand load: grid sizes / k-splits with
+    odd batch sizes (a warp's second camera missing), multi-batch CTAs and a single camera per CTA."""
+    rng = np.random.default_rng(17)
+    N = 97
+    Q = rand_psd(3 * N, rng) + 0.1 * rng.standard_normal((3 * N, 3 * N))
+    X = rng.standard_normal((3 * N, r))
+    h = gpu_handle_factory(grid_ctas=grid, ksplit=ks)
+    h.set_q_dense(Q)
+    assert rel(h.qy(X), Q @ X) < TOL
+    assert rel(h.qy(-X, alpha=0.5), -0.5 * Q @ X) < TOL
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_solver_paths_agree(gpu_handle_factory, variant):
     from xm_code_b200 import problems

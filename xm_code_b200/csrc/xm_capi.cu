@@ -467,7 +467,8 @@ static int make_map(xm_handle* h, CUtensorMap* m, const double* base, uint64_t c
 static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     Plan p{};
     p.RP = rank_pad(r);
-    p.NT = (p.RP <= 10) ? 512 : 256;                   // dense sweeps hold 3 x RP accumulators per lane
+    p.NT = (p.RP <= 6) ? 512 : 256;                    // dense sweeps hold 3 x RP accumulators per lane (6 x RP at RP = 8, 10: two cameras per warp)
+    if (p.RP >= 8 && p.RP <= 10) { if (const char* e = getenv("XM_TUNE_DENSE_NT")) { if (atoi(e) == 512) p.NT = 512; } }      // A/B hook: one camera per warp
     if (h->is_bsr) {
         // block-CSR holds 3 accumulators per lane whatever the rank; the operand gather is latency-bound, so resident warps
         // matter more than registers: 1024 threads (32 warps, <= 64 registers, 16-block chunks, 2 gathers in flight per sub-warp)
@@ -491,14 +492,15 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     if (const char* e = getenv("XM_TUNE_NPROD")) { int v = atoi(e); if (p.use_tma && v >= 1 && v <= 4) p.nprod = v; }     // tuning hook
     const int nwork = p.NW - p.nprod;                   // warps that stream
     p.NWC = nwork;
+    const int cams = p.use_tma ? dense_cams_per_warp(p.RP, p.NT) : 1;      // cameras per consumer warp (xm_device.cuh)
     p.KC = kKC;     // compile-time chunk width of the TMA ring (xm_device.cuh)
     p.nchunks = (h->ldq + p.KC - 1) / p.KC;
     // k-split: the largest divisor KS of nwork with KS * cpc <= nwork (or the caller's cap), at most one chunk/step each
     const int kmax = p.use_tma ? p.nchunks : (h->is_bsr ? nwork : std::max(1, h->ldq / 64));
     int KS = 1;
     for (int k = 1; k <= nwork; ++k)
-        if (nwork % k == 0 && k <= kmax && ((h->opt.ksplit > 0) ? (k <= h->opt.ksplit) : (k * cpc <= nwork))) KS = k;
-    p.KS = KS; p.CB = nwork / KS;
+        if (nwork % k == 0 && k <= kmax && ((h->opt.ksplit > 0) ? (k <= h->opt.ksplit) : (k * cpc <= nwork * cams))) KS = k;
+    p.KS = KS; p.CB = nwork / KS * cams;
     p.cpc = cpc; p.GT = GT;
     // per-CTA state vectors in shared memory when they are small (kills the L2 round trips of every per-camera phase)
     size_t budget = (size_t)std::min(h->smem_optin, 227 * 1024) - 12 * 1024;               // static smem + slack

@@ -27,6 +27,11 @@ constexpr int kBsrChunkMax = 32;    // block-CSR: blocks per staged chunk <= 32 
                                     // one 4 KB bulk copy per chunk) or 16 (1024-thread CTAs: 32 warps x 2 buffers x 2 KB fit shared memory)
 constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node that can share a solve (camera partition, peer-mapped exchange)
 
+// Dense TMA path: cameras (3-row groups of Q) one consumer warp sweeps per operand load.  Per 64 columns a warp issues 3 CAMS + r
+// LDS.128 for 6 r CAMS DFMA: at r >= 8 one camera per warp is bound by shared-memory bandwidth (13 loads per 60 DFMA at r = 10), two
+// cameras per warp (16 loads per 120 DFMA) are not — at the price of 6 x RP accumulators per lane, hence 256-thread CTAs there.
+__host__ __device__ constexpr int dense_cams_per_warp(int RP, int NT) { return (NT == 256 && RP >= 8 && RP <= 10) ? 2 : 1; }
+
 enum Mode : int { MODE_OUT = 0, MODE_OBJ = 1, MODE_HESS = 2 };
 enum VecId : int { V_Y = 0, V_YNEW, V_D, V_DNEW, V_EG, V_RG, V_P, V_RR, V_V, V_HV, V_HP, V_E, kNumVecR };   // V_E: 2 Q X(p) (e_rec only)
 enum ScaId : int { S_S = 0, S_SNEW, S_GS, S_RGS, S_PS, S_RS, S_VS, S_HVS, S_HPS, kNumVecS };
@@ -741,6 +746,39 @@ __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, b
     }
 }
 
+// One block row through the chunk pipeline as a NON-INLINED function with a minimal context: inside the persistent kernels the
+// gather loop otherwise shares its 64 registers (1024-thread CTAs) with everything the kernel keeps alive across the Q.Y phase and
+// spills ~70 local-memory operations per 16-block chunk (SASS, round 2); behind a call boundary the allocator sees only the loop —
+// the caller's live state is saved once per ROW (~100 blocks) instead.  Same code path as the inlined one (bsr_issue / bsr_consume).
+struct BsrLite {             // what bsr_issue / bsr_consume read from their context
+    const Dev& d;
+    int lane, cpw, sw, j; bool act;
+    double* bsr_buf; unsigned long long* bsr_bar; unsigned bsr_phase;
+};
+struct BsrPipe { BsrCursor cur; int col_cur, buf_cur; };     // the warp's pipeline state, carried from row to row
+template <int K>
+__device__ __noinline__ void bsr_row_product(const Dev& d, int lane, int W, double* buf, unsigned long long* bar, unsigned* phase_io,
+                                             BsrPipe* pipe, int cam, int cam_hi, int CB, unsigned long long policy, double* E_out) {
+    BsrLite c{d, lane, 32 / W, lane / W, lane % W, (lane % W) < d.r, buf, bar, *phase_io};
+    BsrCursor cur = pipe->cur;
+    int col_cur = pipe->col_cur, buf_cur = pipe->buf_cur;
+    double E[3] = {0.0, 0.0, 0.0};
+    while (cur.valid() && cur.cam == cam) {
+        BsrCursor nxt = cur;
+        nxt.q += 1;
+        bsr_seek(d, nxt, cam_hi, 0, CB);
+        int col_nxt = 0;
+        if (nxt.valid()) col_nxt = bsr_issue(c, nxt, buf_cur ^ 1, policy);
+        bsr_consume<K>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
+        cur = nxt; col_cur = col_nxt; buf_cur ^= 1;
+    }
+    for (int off = W; off < 32; off <<= 1) {      // fixed-order butterfly over the warp's sub-warps: every lane gets its column's total
+        E[0] += shfl_xor_d(E[0], off); E[1] += shfl_xor_d(E[1], off); E[2] += shfl_xor_d(E[2], off);
+    }
+    E_out[0] = E[0]; E_out[1] = E[1]; E_out[2] = E[2];
+    pipe->cur = cur; pipe->col_cur = col_cur; pipe->buf_cur = buf_cur; *phase_io = c.bsr_phase;
+}
+
 // ------------------------------------------------------------------------------------------------ per-camera epilogues
 struct ObjArgs { const double* Ycur; const double* scur; double* Dout; };
 
@@ -856,6 +894,19 @@ __device__ __forceinline__ void warp_reduce_to_red(Ctx<RP, NT, MG>& c, double (&
             if (c.lane == 0) c.red[(c.warp * 3 + a) * RP + jj] = v;
         }
 }
+// CAMS cameras per warp (dense TMA path): camera slot q = cslot * CAMS + h of the batch, k-split part ks -> red[(q * KS + ks)][3][RP]
+template <int RP, int NT, bool MG, int CAMS>
+__device__ __forceinline__ void warp_reduce_to_red_cams(Ctx<RP, NT, MG>& c, double (&acc)[3 * CAMS][RP], int cslot, int ks, int KS) {
+#pragma unroll
+    for (int h = 0; h < CAMS; ++h)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int jj = 0; jj < RP; ++jj) {
+                const double v = warpsum(acc[3 * h + a][jj]);
+                if (c.lane == 0) c.red[(((cslot * CAMS + h) * KS + ks) * 3 + a) * RP + jj] = v;
+            }
+}
 
 // ---- direct-load paths: dense without TMA (BSR = false) and block-CSR (BSR = true): all warps of the CTA stream
 template <int RP, int NT, int MODE, bool BSR, bool MG>
@@ -884,22 +935,12 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
         // CTA-wide barrier per batch, so a long row does not hold up 31 other warps and the chunk pipeline never drains
         // (measured on ER-100k: the per-batch barriers cost 20-45 % of the product at 1024 threads).  Sub-warp 0 of the warp runs
         // the epilogue, the other sub-warps shadow it without storing (they hold the same totals).
+        BsrPipe pipe{cur, col_cur, buf_cur};
+        unsigned phase = c.bsr_phase;                        // (a local: taking a Ctx member's address would push the whole context to memory)
+        constexpr int K = (NT >= 1024) ? 2 : 4;              // gathers in flight per sub-warp (tools/bsr_tune.cu: 2 at 32 warps, 4 at 16)
         for (int cam = c.cam_lo + cslot; cam < c.cam_hi; cam += CB) {          // warp-uniform
-            double E[3] = {0.0, 0.0, 0.0};
-            while (cur.valid() && cur.cam == cam) {
-                BsrCursor nxt = cur;
-                nxt.q += 1;
-                bsr_seek(d, nxt, c.cam_hi, 0, CB);
-                int col_nxt = 0;
-                if (nxt.valid()) col_nxt = bsr_issue(c, nxt, buf_cur ^ 1, policy);
-                if (d.bsr_k == 2)      bsr_consume<2>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
-                else if (d.bsr_k == 8) bsr_consume<8>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
-                else                   bsr_consume<4>(c, cur.count(), buf_cur, col_cur, nxt.valid(), E);
-                cur = nxt; col_cur = col_nxt; buf_cur ^= 1;
-            }
-            for (int off = c.W; off < 32; off <<= 1) {      // fixed-order butterfly over the warp's sub-warps: every lane gets its column's total
-                E[0] += shfl_xor_d(E[0], off); E[1] += shfl_xor_d(E[1], off); E[2] += shfl_xor_d(E[2], off);
-            }
+            double E[3];
+            bsr_row_product<K>(d, c.lane, c.W, c.bsr_buf, c.bsr_bar, &phase, &pipe, cam, c.cam_hi, CB, policy, E);
             const bool valid = (c.sw == 0);
             if (MODE == MODE_OUT) {
                 const double o[3] = {d.qy_alpha * E[0], d.qy_alpha * E[1], d.qy_alpha * E[2]};
@@ -910,6 +951,7 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
                 part += epi_obj<RP, NT, MG>(c, cam, E, oa, valid);
             }
         }
+        c.bsr_phase = phase;
         return part;
     }
     for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
@@ -1019,19 +1061,18 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
         if (!ok && c.lane == 0) c.raise_abort();
     } else {
         // ------------------------------------------------ consumers
+        constexpr int CAMS = dense_cams_per_warp(RP, NT);    // cameras per warp: their 3 CAMS rows share every operand load
         const int cslot = c.warp / KS, ks = c.warp % KS;
         const unsigned ring_s = smem_u32(c.ring);
         const unsigned stage_bytes = (unsigned)(stage_doubles * sizeof(double));
         const unsigned row_bytes = (unsigned)(KC * sizeof(double));
         bool ok = true;
-        int chk = (int)((g0 % (unsigned)KS));                // chunk -> k-split owner by running counter (no modulo per chunk)
-        (void)chk;
         for (int bi = 0; bi < nbatches && ok; ++bi) {
             const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
-            const bool has = cslot < nb;
-            double acc[3][RP];
+            const bool has = cslot * CAMS < nb;              // a second camera beyond the batch reads in-bounds stale rows into sums nobody uses
+            double acc[3 * CAMS][RP];
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+            for (int a = 0; a < 3 * CAMS; ++a)
 #pragma unroll
                 for (int jj = 0; jj < RP; ++jj) acc[a][jj] = 0.0;
             int own = 0;                                     // own == ks  <=>  ch % KS == ks
@@ -1044,25 +1085,25 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
                 c.tr(100 + ch);
                 unsigned long long tw1 = 0; if (tm) { tw1 = gtimer(); if (bi == 0 && ch == 0) c.dbg0 += tw1 - tw0; else c.dbg1 += tw1 - tw0; }
                 if (has && own == ks) {
-                    const unsigned q0 = ring_s + (unsigned)s * stage_bytes + (unsigned)(3 * cslot) * row_bytes + (unsigned)(2 * c.lane) * 8u;
+                    const unsigned q0 = ring_s + (unsigned)s * stage_bytes + (unsigned)(3 * CAMS * cslot) * row_bytes + (unsigned)(2 * c.lane) * 8u;
                     const unsigned xs = ring_s + (unsigned)s * stage_bytes + (unsigned)(xoff * sizeof(double)) + (unsigned)(2 * c.lane) * 8u;
                     // All RP operand columns are processed without predicates: for r < RP the extra rows of the stage's operand
                     // area hold stale (in-bounds) data and feed accumulators nobody reads.  Loads first, then the FMAs.
 #pragma unroll
                     for (int k0 = 0; k0 < kKC; k0 += 64) {
-                        double2 a[3], x[RP];
+                        double2 a[3 * CAMS], x[RP];
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) a[q] = lds_v2(q0 + (unsigned)q * row_bytes + k0 * 8);
+                        for (int q = 0; q < 3 * CAMS; ++q) a[q] = lds_v2(q0 + (unsigned)q * row_bytes + k0 * 8);
 #pragma unroll
                         for (int jj = 0; jj < RP; ++jj) x[jj] = lds_v2(xs + (unsigned)jj * row_bytes + k0 * 8);
 #pragma unroll
                         for (int jj = 0; jj < RP; ++jj)
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) acc[q][jj] = fma(a[q].x, x[jj].x, acc[q][jj]);
+                            for (int q = 0; q < 3 * CAMS; ++q) acc[q][jj] = fma(a[q].x, x[jj].x, acc[q][jj]);
 #pragma unroll
                         for (int jj = 0; jj < RP; ++jj)
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) acc[q][jj] = fma(a[q].y, x[jj].y, acc[q][jj]);
+                            for (int q = 0; q < 3 * CAMS; ++q) acc[q][jj] = fma(a[q].y, x[jj].y, acc[q][jj]);
                     }
                 }
                 if (++own == KS) own = 0;
@@ -1072,7 +1113,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
             }
             c.tr(200);
             unsigned long long te0 = 0; if (d.profile && blockIdx.x == 0 && c.tid == 0) te0 = gtimer();
-            warp_reduce_to_red<RP, NT>(c, acc);
+            warp_reduce_to_red_cams<RP, NT, MG, CAMS>(c, acc, cslot, ks, KS);
             named_bar_sync(1, NWC * 32);                    // consumers only: the producer is busy re-arming the ring
             part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, nb, KS, CB);
             named_bar_sync(1, NWC * 32);

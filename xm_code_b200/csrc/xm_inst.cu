@@ -36,6 +36,7 @@ static cudaError_t launch_rp(int kind, const xm_handle* h, const Dev& d, int opc
     if (d.NW == 32) return launch_t<RP, 1024>(kind, h, d, opcode, dyn, st);
     return launch_t<RP, 512>(kind, h, d, opcode, dyn, st);
 #else
+    if (NT_DENSE == 256 && RP <= 10 && d.NW == 16) return launch_t<RP, (RP <= 10 ? 512 : 256)>(kind, h, d, opcode, dyn, st);   // A/B hook: one camera per warp
     return launch_t<RP, NT_DENSE>(kind, h, d, opcode, dyn, st);
 #endif
 }
@@ -53,8 +54,8 @@ cudaError_t XM_GROUP_FN(0, XM_INST_PATH)(int kind, int RP, const xm_handle* h, c
 cudaError_t XM_GROUP_FN(1, XM_INST_PATH)(int kind, int RP, const xm_handle* h, const Dev& d, int opcode, size_t dyn, cudaStream_t st) {
     switch (RP) {
         case 6: return launch_rp<6, 512>(kind, h, d, opcode, dyn, st);
-        case 8: return launch_rp<8, 512>(kind, h, d, opcode, dyn, st);
-        case 10: return launch_rp<10, 512>(kind, h, d, opcode, dyn, st);
+        case 8: return launch_rp<8, 256>(kind, h, d, opcode, dyn, st);
+        case 10: return launch_rp<10, 256>(kind, h, d, opcode, dyn, st);
     }
     return cudaErrorInvalidValue;
 }

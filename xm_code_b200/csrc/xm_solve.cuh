@@ -259,7 +259,7 @@ __device__ __forceinline__ double phase_model_retract(Ctx<RP, NT, MG>& c, const 
 template <int RP, int NT, int PATH, bool MG>
 __global__ void __launch_bounds__(NT, 1) xm_solve_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
                                                          const __grid_constant__ CUtensorMap mapX) {
-    __shared__ double red[(NT / 32) * 3 * RP];
+    __shared__ double red[(NT / 32) * 3 * RP * dense_cams_per_warp(RP, NT)];
     __shared__ double bsum[NT / 32];
     __shared__ double bcast[4];
     extern __shared__ unsigned char dyn_smem[];
@@ -568,7 +568,7 @@ xm_abort:
 template <int RP, int NT, int PATH, bool MG>
 __global__ void __launch_bounds__(NT, 1) xm_ops_kernel(const __grid_constant__ Dev d, const __grid_constant__ QMaps mapsQ,
                                                        const __grid_constant__ CUtensorMap mapX, const int opcode) {
-    __shared__ double red[(NT / 32) * 3 * RP];
+    __shared__ double red[(NT / 32) * 3 * RP * dense_cams_per_warp(RP, NT)];
     __shared__ double bsum[NT / 32];
     __shared__ double bcast[4];
     extern __shared__ unsigned char dyn_smem[];
