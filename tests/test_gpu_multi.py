@@ -308,7 +308,7 @@ def test_boundary_only_exchange_on_a_banded_view_graph(team_factory, monkeypatch
     for got in res:
         assert got.stats["outer_iters"] == ref.outer_iters
         assert abs(got.primal - ref.primal) <= 1e-7 * abs(ref.primal)         # a point far from convergence: rounding moves it at the 1e-9 level
-        np.testing.assert_allclose(got.s, ref.s, atol=1e-6, rtol=0)
+        np.testing.assert_allclose(got.s, ref.s, atol=1e-5, rtol=0)
     X = rng.standard_normal((3 * N, 4))
     for got in t.call("qy", X, 1.0):
         assert rel(got, Q @ X) < TOL

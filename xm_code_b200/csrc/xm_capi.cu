@@ -472,9 +472,9 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     if (h->is_bsr) {
         // block-CSR holds 3 accumulators per lane whatever the rank; the operand gather is latency-bound, so resident warps
         // matter more than registers: 1024 threads (32 warps, <= 64 registers, 16-block chunks, 2 gathers in flight per sub-warp)
-        // measured 8 / 21 / 23 % faster than 512 threads at r = 5 / 10 / 20 on ER-100k (profiles/r02_bsr_tune.txt)
-        p.NT = 1024;
-        if (const char* e = getenv("XM_TUNE_BSR_NT")) { if (atoi(e) == 512) p.NT = 512; }             // A/B hook
+        // measured 8 / 21 / 23 % faster than 512 threads at r = 5 / 10 / 20 in the standalone experiment (profiles/r02_bsr_tune.txt)
+        p.NT = (r <= 5) ? 512 : 1024;      // in-library (profiles/r02_bsr_er100k_*): 512 threads win at r <= 5, 1024 at r >= 10
+        if (const char* e = getenv("XM_TUNE_BSR_NT")) { const int v = atoi(e); if (v == 512 || v == 1024) p.NT = v; }             // A/B hook
     }
     p.NW = p.NT / 32;
     p.W = 4; while (p.W < r) p.W <<= 1;
