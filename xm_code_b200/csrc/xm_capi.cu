@@ -510,17 +510,23 @@ static Plan make_plan(const xm_handle* h, int r, int allow_tma = 1) {
     p.dyn_smem = (p.vec_smem ? p.vec_bytes : 0) + 256;
     if (h->is_bsr) p.dyn_smem += (size_t)p.NW * 2 * ((p.NT == 1024 ? 16 : 32) * 128 + 8);      // per-warp staging of the block chunks (xm_device.cuh: bsr_issue)
     if (p.use_tma) {
-        p.nbmax = std::min(p.CB, cpc);
+        // batch heights that occur: CTAs own q or q+1 cameras, swept in EVEN batches (xm_device.cuh: Batches) — at most three distinct sizes
+        const int q = h->N / GT;
+        int nsz = 0;
+        auto add = [&](int v) { if (v <= 0) return; for (int t = 0; t < nsz; ++t) if (p.box_nb[t] == v) return; if (nsz < 3) p.box_nb[nsz++] = v; };
+        for (int n = q; n <= q + 1; ++n) {
+            if (n <= 0) continue;
+            const int nbat = (n + p.CB - 1) / p.CB, base = n / nbat;
+            add(base + (n % nbat ? 1 : 0)); add(base);
+        }
+        while (nsz < 3) { p.box_nb[nsz] = p.box_nb[0]; ++nsz; }
+        p.nbmax = std::max(p.box_nb[0], std::max(p.box_nb[1], p.box_nb[2]));
         p.stage_doubles = (3 * p.nbmax + p.RP) * p.KC;   // operand area sized for the padded rank (consumers read RP rows)
         int ST = (int)((budget - 1024) / ((size_t)p.stage_doubles * sizeof(double)));
         ST = std::min(ST, 24);
         if (const char* e = getenv("XM_TUNE_ST")) { int v = atoi(e); if (v >= 2) ST = std::min(ST, v); }                      // tuning hook
         if (ST < 2) return make_plan(h, r, 0);          // ring does not fit: direct streaming loads
         p.ST = ST;
-        // batch heights that occur: CTAs own q or q+1 cameras; full batches have CB cameras, a CTA's last batch the rest
-        auto last = [&](int n) { return n <= 0 ? p.CB : n - ((n - 1) / p.CB) * p.CB; };
-        const int q = h->N / GT;
-        p.box_nb[0] = std::min(p.CB, cpc); p.box_nb[1] = last(q); p.box_nb[2] = last(q + 1);
         p.dyn_smem += (size_t)ST * p.stage_doubles * sizeof(double) + 3 * ST * sizeof(unsigned long long);
     }
     return p;

@@ -853,6 +853,20 @@ __device__ __forceinline__ double epi_obj(Ctx<RP, NT, MG>& c, int i, const doubl
     return part;
 }
 
+// A CTA's cameras are swept in batches of at most CB cameras (one TMA box per batch and chunk).  The batches are EVEN: ncam cameras in
+// nbat = ceil(ncam / CB) batches of floor(ncam / nbat) or one more — a short tail batch (92 = 6 x 15 + 2) costs almost a full batch's
+// time, because a TMA box of 6 rows is op-rate bound, not bandwidth bound (measured: 9-row boxes run at half the rate of 45-row boxes).
+struct Batches {
+    int lo, n, nbat, base, rem, cb;         // cb > 0: uniform batches of cb cameras + a tail (the block-CSR chunk cursor strides by cb)
+    __device__ __forceinline__ Batches(int cam_lo, int cam_hi, int CB, bool even) {
+        n = cam_hi - cam_lo;
+        lo = cam_lo; nbat = (n + CB - 1) / CB; if (nbat < 1) nbat = 1;
+        base = n / nbat; rem = n - base * nbat; cb = even ? 0 : CB;
+    }
+    __device__ __forceinline__ int first(int bi) const { return cb ? lo + bi * cb : lo + bi * base + min(bi, rem); }
+    __device__ __forceinline__ int count(int bi) const { return cb ? min(cb, n - bi * cb) : base + (bi < rem ? 1 : 0); }
+};
+
 // ------------------------------------------------------------------------------------------------ fused Q.Y phase
 // Per-batch tail shared by both dense paths and the BSR path: `red` holds, per warp, the 3*RP sums of its (camera,
 // k-split) task; sub-warp slot q finishes batch camera q: adds the KS partial sums in fixed order and runs the
@@ -973,8 +987,10 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
         c.bsr_phase = phase;
         return part;
     }
-    for (int b0 = c.cam_lo; b0 < c.cam_hi; b0 += CB) {      // CTA-uniform loop
-        const int cam = b0 + cslot;
+    const Batches bt(c.cam_lo, c.cam_hi, CB, !BSR);
+    for (int bi = 0; bi < bt.nbat; ++bi) {                  // CTA-uniform loop
+        const int b0 = bt.first(bi), nbv = bt.count(bi);
+        const int cam = (cslot < nbv) ? b0 + cslot : c.cam_hi;      // slots beyond the batch idle (cam_hi: "no camera")
         if (BSR) {
             double E[3] = {0.0, 0.0, 0.0};
             while (cur.valid() && cur.cam == cam) {                            // warp-uniform
@@ -1004,7 +1020,7 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
             warp_reduce_to_red<RP, NT>(c, acc);
         }
         __syncthreads();
-        part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, min(CB, c.cam_hi - b0), KS, CB);
+        part += qy_batch_epilogue<RP, NT, MODE>(c, oa, b0, nbv, KS, CB);
         __syncthreads();
     }
     return part;
@@ -1023,7 +1039,8 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
     const int KS = d.KS, CB = d.CB, ST = d.ST, nchunks = d.nchunks;
     constexpr int KC = kKC;
     const int ncam = c.cam_hi - c.cam_lo;
-    const int nbatches = (ncam + CB - 1) / CB;
+    const Batches bt(c.cam_lo, c.cam_hi, CB, true);
+    const int nbatches = bt.nbat;
     const int uses = nbatches * nchunks;
     const unsigned g0 = c.g_use;
     const int pre = c.prefetched;
@@ -1047,7 +1064,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
                                                             // (parity waits cannot tell phase k from k+2, so a stage must never have two issuers)
             const int uu = spec ? u - uses : u;
             const int bi = uu / nchunks, ch = uu - bi * nchunks;
-            const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
+            const int b0 = bt.first(bi), nb = bt.count(bi);
             double* st = c.ring + (size_t)s * stage_doubles;
             if (spec || u >= pre) {                         // Q tiles not in flight yet
                 if (g >= (unsigned)ST) {                    // stage must have been released by every consumer warp
@@ -1072,7 +1089,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
         if (ok && prefetch_next && c.lane == 0 && pw == 0) {
             for (int uu = npre; uu < npre + d.l2_prefetch && uu < uses; ++uu) {
                 const int bi = uu / nchunks, ch = uu - bi * nchunks;
-                const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
+                const int b0 = bt.first(bi), nb = bt.count(bi);
                 const CUtensorMap* mq = (nb == d.box_nb[0]) ? mapQ3 : (nb == d.box_nb[1]) ? mapQ3 + 1 : mapQ3 + 2;
                 tma_prefetch_l2_2d(mq, ch * KC, 3 * b0 - d.row0);
             }
@@ -1087,7 +1104,7 @@ __device__ __forceinline__ double qy_phase_tma(Ctx<RP, NT, MG>& c, const ObjArgs
         const unsigned row_bytes = (unsigned)(KC * sizeof(double));
         bool ok = true;
         for (int bi = 0; bi < nbatches && ok; ++bi) {
-            const int b0 = c.cam_lo + bi * CB, nb = min(CB, c.cam_hi - b0);
+            const int b0 = bt.first(bi), nb = bt.count(bi);
             const bool has = cslot * CAMS < nb;              // a second camera beyond the batch reads in-bounds stale rows into sums nobody uses
             double acc[3 * CAMS][RP];
 #pragma unroll
