@@ -5,10 +5,11 @@ Workload (BASELINE.json config 4, the bandwidth-bound regime the path is built f
 (13 682 cameras, 3N = 41 046, Q = 13.5 GB FP64), built ON THE DEVICE by a plain-torch generator shared by both arms
 (xm_code_b200/problems.py: synthetic_sfm_torch + q_from_observations_torch — deterministic, ~4 s).  One "step" = one
 XMtrustregion-equivalent call at rank 3 from the reference's identity start with gradtol 1e-6 and the reference's own time
-limit `maxtime` = 4 s (XM/include/XM/trustregion.h:77, time exit :538-543).  A full solve to the KKT tolerance is 6 735 tCG
+limit `maxtime` = 4 s (XM/include/XM/trustregion.h:77, time exit :538-543).  A full solve to the KKT tolerance is ~7 000 tCG
 iterations here (16 s on one B200, ~55 s for the reference): 25 of those per arm do not fit a bench run, so every step runs
-the first 4 s of that solve and the metric is the rate, tCG iterations per second (each iteration = one Q.Y over all of Q
-+ the fused per-camera work).  The full time-to-KKT is measured once per run and reported in `result.full_solve`.
+the first 4 s of that solve (the whole solve where it takes less: 2.1 s on 8 GPUs) and the metric is the rate, tCG iterations
+per second (each iteration = one Q.Y over all of Q + the fused per-camera work).  The full time-to-KKT is measured once per
+run and reported in `result.full_solve`; `result.bsr_er100k` is BASELINE config 5 (block-CSR) on the same GPUs.
 XM_BENCH_CAMERAS=<n> changes the camera count; below 4000 cameras (e.g. 1723 = BAL-Ladybug, the round-1 workload, 214 MB)
 the NumPy generator is used and a step is a FULL solve.
 
