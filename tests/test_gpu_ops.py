@@ -145,3 +145,38 @@ def test_bsr_operator_matches_dense(gpu_handle_factory):
         assert rel(h.qy(X, 0.5), 0.5 * Q @ X) < TOL
     Y, s = rand_point(120, 4, rng)
     assert abs(h.objective(xo.from_blocks(Y), s, 0.0) - xo.objective(Q, Y, s, 0.0)) < 1e-11 * abs(xo.objective(Q, Y, s, 0.0))
+
+
+@pytest.mark.parametrize("r", [3, 5, 8, 20])
+def test_bsr_ragged_rows_and_4x4_blocks(gpu_handle_factory, r):
+    """Block-CSR edge cases through both thread geometries (512 threads at r <= 5, 1024 above): empty block rows, single-block rows,
+    row lengths at and around the staged chunk sizes (16 / 32 blocks) and far beyond them, unsorted column order inside a row, and the
+    4x4-block input form (one 4x4 block per view-graph edge: only the leading 3x3 acts on the rotation rows)."""
+    rng = np.random.default_rng(60 + r)
+    N = 230
+    lengths = [0, 1, 15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65, 2, 130, 0, 229]
+    rowptr = [0]; col = []
+    for i in range(N):
+        k = lengths[i % len(lengths)]
+        col.extend(rng.permutation(N)[:k].tolist())            # deliberately unsorted
+        rowptr.append(len(col))
+    rowptr = np.array(rowptr, dtype=np.int32); col = np.array(col, dtype=np.int32)
+    blocks = rng.standard_normal((col.size, 3, 3))               # blocks[b][row][col]
+    Q = np.zeros((3 * N, 3 * N))
+    for i in range(N):
+        for b in range(rowptr[i], rowptr[i + 1]):
+            Q[3 * i:3 * i + 3, 3 * col[b]:3 * col[b] + 3] += blocks[b]          # (a permutation has no duplicate columns)
+    X = rng.standard_normal((3 * N, r))
+    h = gpu_handle_factory()
+    h.set_q_bsr(rowptr, col, np.ascontiguousarray(np.swapaxes(blocks, 1, 2)), 3)     # wire format: column-major inside a block
+    got = h.qy(X, alpha=1.5)
+    assert rel(got, 1.5 * Q @ X) < TOL
+    empty = [i for i in range(N) if rowptr[i] == rowptr[i + 1]]
+    assert empty
+    for i in empty:
+        assert np.all(got[3 * i:3 * i + 3] == 0.0)
+    b4 = np.zeros((col.size, 4, 4)); b4[:, :3, :3] = blocks
+    b4[:, 3, :] = rng.standard_normal((col.size, 4)); b4[:, :, 3] = rng.standard_normal((col.size, 4))     # translation parts: ignored
+    h4 = gpu_handle_factory()
+    h4.set_q_bsr(rowptr, col, np.ascontiguousarray(np.swapaxes(b4, 1, 2)), 4)
+    assert rel(h4.qy(X, alpha=1.5), 1.5 * Q @ X) < TOL

@@ -32,7 +32,7 @@ if "single" in WHAT:
     for kw in (dict(), dict(qy_variant=1), dict(vec_in_global=True), dict(three_barrier_tcg=True)):
         h = capi.Handle(device=0, **kw)
         h.set_q_dense(Q2)
-        for r in (3, 5, 12):
+        for r in (3, 5, 8, 10, 12):          # 8 / 10: two cameras per consumer warp (256-thread CTAs)
             X = rng.standard_normal((3 * N, r))
             assert rel(h.qy(X), Q2 @ X) < 1e-12
         got = h.trust_region(xo.from_blocks(xo.identity_init(N, 3)), np.ones(N), 0.0, 1e-6)
@@ -41,6 +41,9 @@ if "single" in WHAT:
         h.close()
     h = capi.Handle(device=0)
     h.set_q_dense(Q2)
+    Y10 = xo.mgs_rows(rng.standard_normal((N, 3, 10)))
+    g10 = h.trust_region(xo.from_blocks(Y10), np.ones(N), 0.0, 1e-6)
+    print("solve r=10", g10.primal, g10.stats["tcg_iters"], g10.stats["threads_per_cta"], flush=True)
     Y = xo.mgs_rows(rng.standard_normal((N, 3, 4))); s = np.concatenate([[1.0], rng.uniform(0.8, 1.2, N - 1)])
     R = xo.from_blocks(Y)
     h.objective(R, s, 0.1); h.rgrad(R, s, 0.1)
