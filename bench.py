@@ -132,14 +132,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+SOLVE_KERNEL_SOURCES = ("xm_device.cuh", "xm_solve.cuh", "xm_inst.cu", "xm_capi.cu", "xm_host.h", "../../include/xm_b200.h")
+
+
 def source_hash():
-    """Hash of the library's sources (csrc + the C header): identifies the build an ncu capture belongs to."""
+    """Hash of the sources that define the persistent solve kernel and its launch plan: identifies the build an ncu capture belongs to."""
     import hashlib
     hsh = hashlib.sha256()
     d = os.path.join(ROOT, "xm_code_b200", "csrc")
-    for f in sorted(os.listdir(d)) + ["../../include/xm_b200.h"]:
-        if f.endswith((".cu", ".cuh", ".h")):
-            hsh.update(open(os.path.join(d, f), "rb").read())
+    for f in SOLVE_KERNEL_SOURCES:
+        hsh.update(open(os.path.join(d, f), "rb").read())
     return hsh.hexdigest()[:16]
 
 

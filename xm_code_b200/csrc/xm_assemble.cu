@@ -168,8 +168,9 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     double* dl = mem.get<double>(M); double* Sc = mem.get<double>((size_t)N * N); double* B = mem.get<double>((size_t)n3 * N); int* info = mem.get<int>(1);
     if (!d_cam || !d_lm || !d_w || !d_pt || !d_lm_ptr || !d_lm_obs || !d_cam_ptr || !d_cam_obs || !dl || !Sc || !B || !info) { h->err = "assembly workspace cudaMalloc failed"; return XM_ENOMEM; }
     cudaStream_t st = h->stream;
-    cudaEvent_t ev0, ev1;
-    ASM_CUDA(cudaEventCreate(&ev0)); ASM_CUDA(cudaEventCreate(&ev1));
+    struct Events { cudaEvent_t a = nullptr, b = nullptr; ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evs;    // freed on every exit path
+    ASM_CUDA(cudaEventCreate(&evs.a)); ASM_CUDA(cudaEventCreate(&evs.b));
+    cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     ASM_CUDA(cudaEventRecord(ev0, st));
     ASM_CUDA(cudaMemcpyAsync(d_cam, cam, n_obs * sizeof(int), cudaMemcpyHostToDevice, st));
     ASM_CUDA(cudaMemcpyAsync(d_lm, lm, n_obs * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -232,7 +233,6 @@ extern "C" int xm_create_matrix(xm_handle* h, int n_cameras, int n_landmarks, in
     mark("Abar + copies out");
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (assemble_ms_out) *assemble_ms_out = ms;
     h->n3 = n3; h->N = N; h->ldq = ldq; h->is_bsr = false; h->cam0 = 0; h->cam1 = N;
     return XM_OK;

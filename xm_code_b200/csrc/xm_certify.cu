@@ -414,8 +414,9 @@ extern "C" int xm_certify_ex(xm_handle* h, int r, const double* R, const double*
     if (method == XM_CERT_DENSE && (h->is_bsr || h->world > 1)) { h->err = "the dense certificate needs a dense Q on one GPU (use XM_CERT_ITERATIVE)"; return XM_EUNSUPPORTED; }
     if (method != XM_CERT_DENSE && method != XM_CERT_ITERATIVE) return XM_EINVAL;
     XM_CUDA(h, cudaSetDevice(h->device));
-    cudaEvent_t e0, e1;
-    XM_CUDA(h, cudaEventCreate(&e0)); XM_CUDA(h, cudaEventCreate(&e1));
+    struct Events { cudaEvent_t a = nullptr, b = nullptr; ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } ev;     // freed on every exit path
+    XM_CUDA(h, cudaEventCreate(&ev.a)); XM_CUDA(h, cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     XM_CUDA(h, cudaEventRecord(e0, h->stream));
     DevBuf mem(h->stream);
     const size_t col = (size_t)n3;
@@ -476,7 +477,6 @@ extern "C" int xm_certify_ex(xm_handle* h, int r, const double* R, const double*
     CERT_CUDA(cudaStreamSynchronize(h->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double gap = primal - dual - 3.0 * N * std::fmin(0.0, w0);      // :334-336 (bar_s = 1)
     const double bound = (N > 2000) ? 1e-3 : 1e-4;                         // :349-358 (later tiers unreachable, quirk Q5)
     const int certified = (gap / primal < 1e-3 || w0 > -bound) ? 1 : 0;    // :360
