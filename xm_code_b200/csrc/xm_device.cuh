@@ -135,6 +135,14 @@ __device__ __forceinline__ double2 ldg_stream_v2(const double* p) {
     return v;
 }
 
+// plain (coherent) global load through an explicit state space: inside a non-inlined device function a pointer argument is generic
+// for the compiler (LD.E + address-space resolution); the operand changes between phases, so the read-only .nc path is not an option
+__device__ __forceinline__ double ld_global_f64(const double* p) {
+    double v;
+    asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // one row of a padded 4x4 block: 32 bytes in one request (LDG.E.256)
 __device__ __forceinline__ void ldg_stream_v4(const double* p, double (&v)[4]) {
     asm("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
@@ -676,9 +684,10 @@ struct BsrCursor {           // the warp's position in its sequence of chunks: r
     __device__ __forceinline__ int start() const { return rb0 + q * ch; }
     __device__ __forceinline__ int count() const { return min(ch, rb1 - start()); }
 };
-__device__ __forceinline__ void bsr_seek(const Dev& d, BsrCursor& cu, int cam_hi, int part, int CB) {   // first non-empty chunk at or after (cam, q)
+template <class D>
+__device__ __forceinline__ void bsr_seek(const D& d, BsrCursor& cu, int cam_hi, int part, int CB) {   // first non-empty chunk at or after (cam, q)
     while (cu.cam < cam_hi) {
-        cu.rb0 = d.bsr_rowptr[cu.cam - d.cam0]; cu.rb1 = d.bsr_rowptr[cu.cam - d.cam0 + 1];
+        cu.rb0 = __ldg(d.bsr_rowptr + (cu.cam - d.cam0)); cu.rb1 = __ldg(d.bsr_rowptr + (cu.cam - d.cam0 + 1));
         if (cu.rb0 + cu.q * cu.ch < cu.rb1) return;
         cu.cam += CB; cu.q = part;
     }
@@ -686,7 +695,7 @@ __device__ __forceinline__ void bsr_seek(const Dev& d, BsrCursor& cu, int cam_hi
 }
 template <class C>
 __device__ __forceinline__ int bsr_issue(C& c, const BsrCursor& cu, int buf, unsigned long long policy) {   // returns this lane's column index
-    const Dev& d = c.d;
+    const auto& d = c.d;
     const int st = cu.start(), nb = cu.count();
     __syncwarp();                                            // every lane is done with the buffer's previous chunk
     if (d.bsr_stage == 0) {                                  // one bulk-TMA copy per chunk
@@ -709,7 +718,7 @@ __device__ __forceinline__ int bsr_issue(C& c, const BsrCursor& cu, int buf, uns
 // (more_in_flight: a younger chunk has been committed after this one)
 template <int K, class C>
 __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, bool more_in_flight, double (&E)[3]) {
-    const Dev& d = c.d;
+    const auto& d = c.d;
     const int r = d.r, cpw = c.cpw;
     if (d.bsr_stage == 0) {
         (void)mbar_wait(&c.bsr_bar[buf], (c.bsr_phase >> buf) & 1u);
@@ -729,7 +738,7 @@ __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, b
             x[k][0] = x[k][1] = x[k][2] = 0.0;
             if (c.act && bi < nb) {
                 const double* xp = xc + (size_t)(3 * cc) * r + c.j;
-                x[k][0] = xp[0]; x[k][1] = xp[r]; x[k][2] = xp[2 * r];
+                x[k][0] = ld_global_f64(xp); x[k][1] = ld_global_f64(xp + r); x[k][2] = ld_global_f64(xp + 2 * r);
             }
         }
 #pragma unroll
@@ -750,14 +759,18 @@ __device__ __forceinline__ void bsr_consume(C& c, int nb, int buf, int colreg, b
 // gather loop otherwise shares its 64 registers (1024-thread CTAs) with everything the kernel keeps alive across the Q.Y phase and
 // spills ~70 local-memory operations per 16-block chunk (SASS, round 2); behind a call boundary the allocator sees only the loop —
 // the caller's live state is saved once per ROW (~100 blocks) instead.  Same code path as the inlined one (bsr_issue / bsr_consume).
+struct BsrDev {              // the fields of Dev the block-CSR row product reads, BY VALUE: through a `const Dev&` every access is a generic
+    const int* bsr_rowptr; const int* bsr_col; const double* bsr_val; const double* Xt;      // load from the kernel's parameter block
+    int r, bsr_stage, bsr_chunk, cam0;
+};
 struct BsrLite {             // what bsr_issue / bsr_consume read from their context
-    const Dev& d;
+    BsrDev d;
     int lane, cpw, sw, j; bool act;
     double* bsr_buf; unsigned long long* bsr_bar; unsigned bsr_phase;
 };
 struct BsrPipe { BsrCursor cur; int col_cur, buf_cur; };     // the warp's pipeline state, carried from row to row
 template <int K>
-__device__ __noinline__ void bsr_row_product(const Dev& d, int lane, int W, double* buf, unsigned long long* bar, unsigned* phase_io,
+__device__ __noinline__ void bsr_row_product(const BsrDev d, int lane, int W, double* buf, unsigned long long* bar, unsigned* phase_io,
                                              BsrPipe* pipe, int cam, int cam_hi, int CB, unsigned long long policy, double* E_out) {
     BsrLite c{d, lane, 32 / W, lane / W, lane % W, (lane % W) < d.r, buf, bar, *phase_io};
     BsrCursor cur = pipe->cur;
@@ -950,13 +963,14 @@ __device__ __forceinline__ double qy_phase_direct(Ctx<RP, NT, MG>& c, const ObjA
         // (measured on ER-100k: the per-batch barriers cost 20-45 % of the product at 1024 threads).  Sub-warp 0 of the warp runs
         // the epilogue, the other sub-warps shadow it without storing (they hold the same totals).
         BsrPipe pipe{cur, col_cur, buf_cur};
+        const BsrDev bd{d.bsr_rowptr, d.bsr_col, d.bsr_val, d.Xt, d.r, d.bsr_stage, d.bsr_chunk, d.cam0};
         unsigned phase = c.bsr_phase;                        // (a local: taking a Ctx member's address would push the whole context to memory)
         constexpr int K = (NT >= 1024) ? 2 : 4;              // gathers in flight per sub-warp (tools/bsr_tune.cu: 2 at 32 warps, 4 at 16)
         for (int cam = c.cam_lo + cslot; cam < c.cam_hi; cam += CB) {          // warp-uniform
             double E[3] = {0.0, 0.0, 0.0};
             if (NT >= 1024) {
                 // 64 registers per thread: the row product behind a call boundary (measured: +5-17 % over the inlined loop, which spills)
-                bsr_row_product<K>(d, c.lane, c.W, c.bsr_buf, c.bsr_bar, &phase, &pipe, cam, c.cam_hi, CB, policy, E);
+                bsr_row_product<K>(bd, c.lane, c.W, c.bsr_buf, c.bsr_bar, &phase, &pipe, cam, c.cam_hi, CB, policy, E);
             } else {
                 // 128 registers per thread: nothing to relieve, the inlined loop is ~10 % faster than the call
                 c.bsr_phase = phase;
